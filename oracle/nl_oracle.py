@@ -1,0 +1,181 @@
+"""ctypes binding of the CPU oracle (oracle/libnl_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, by __graft_entry__.smoke() and by bench.py's
+cpu_baseline / --impl reference legs.  Nothing under nonlin_b200/ imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+LM, NEWTON, BROYDEN = 0, 1, 2
+SOLVERS = {"least_squares": LM, "lm": LM, "newton": NEWTON, "quasi_newton": BROYDEN, "broyden": BROYDEN}
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("max_fcn_evals", C.c_int32),
+        ("fcn_tol", C.c_double),
+        ("var_tol", C.c_double),
+        ("grad_tol", C.c_double),
+        ("lm_factor", C.c_double),
+        ("jacobian_interval", C.c_int32),
+        ("use_line_search", C.c_int32),
+        ("ls_max_fcn_evals", C.c_int32),
+        ("ls_alpha", C.c_double),
+        ("ls_factor", C.c_double),
+        ("use_analytic_jacobian", C.c_int32),
+        ("max_iter_guard", C.c_int32),
+    ]
+
+
+IB_DTYPE = np.dtype(
+    [
+        ("iter_count", "<i4"),
+        ("fcn_count", "<i4"),
+        ("jacobian_count", "<i4"),
+        ("gradient_count", "<i4"),
+        ("converge_on_fcn", "<i4"),
+        ("converge_on_chng", "<i4"),
+        ("converge_on_zero_diff", "<i4"),
+    ]
+)
+
+
+def build(force=False):
+    """Compile the oracle with its Makefile (gcc only; no reference sources involved)."""
+    so = os.path.join(_HERE, "libnl_oracle.so")
+    if force or not os.path.exists(so) or not os.path.exists(os.path.join(_HERE, "libnl_oracle_count.so")):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return so
+
+
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+
+
+class Oracle:
+    def __init__(self, counting=False):
+        build()
+        name = "libnl_oracle_count.so" if counting else "libnl_oracle.so"
+        self.lib = lib = C.CDLL(os.path.join(_HERE, name))
+        lib.nlo_fcn_lookup.argtypes = [C.c_char_p]
+        lib.nlo_fcn_lookup.restype = C.c_int
+        lib.nlo_params_default.argtypes = [C.POINTER(Params)]
+        lib.nlo_soft_exp.argtypes = [C.c_double]
+        lib.nlo_soft_exp.restype = C.c_double
+        lib.nlo_norm2.argtypes = [_dp, C.c_int]
+        lib.nlo_norm2.restype = C.c_double
+        lib.nlo_dnrm2.argtypes = [_dp, C.c_int]
+        lib.nlo_dnrm2.restype = C.c_double
+        lib.nlo_flops_total.restype = C.c_ulonglong
+        lib.nlo_solve.restype = C.c_int
+        lib.nlo_solve_batch.restype = C.c_int
+        lib.nlo_eval_fcn.restype = C.c_int
+        lib.nlo_jacobian.restype = C.c_int
+        lib.nlo_dgesv.restype = C.c_int
+
+    # -- registry -----------------------------------------------------------------------
+    def fcn_id(self, name):
+        i = self.lib.nlo_fcn_lookup(name.encode())
+        if i < 0:
+            raise KeyError(name)
+        return i
+
+    def fcn_info(self, fid):
+        v = [C.c_int() for _ in range(5)]
+        if self.lib.nlo_fcn_info(fid, *[C.byref(x) for x in v]) != 0:
+            raise KeyError(fid)
+        return dict(zip(["m", "n", "sys_len", "shared_len", "has_jac"], [x.value for x in v]))
+
+    def params(self, **kw):
+        p = Params()
+        self.lib.nlo_params_default(C.byref(p))
+        for k, v in kw.items():
+            if not hasattr(p, k):
+                raise AttributeError(k)
+            setattr(p, k, v)
+        return p
+
+    def set_libm_exp(self, on):
+        self.lib.nlo_set_libm_exp(int(bool(on)))
+
+    def flops_total(self):
+        return int(self.lib.nlo_flops_total())
+
+    def flops_reset(self):
+        self.lib.nlo_flops_reset()
+
+    # -- helpers ------------------------------------------------------------------------
+    @staticmethod
+    def _ptr(a):
+        return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+    def eval_fcn(self, fcn, x, m=0, sys=None, shared=None):
+        fid = self.fcn_id(fcn) if isinstance(fcn, str) else fcn
+        info = self.fcn_info(fid)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        n = info["n"] or x.size
+        m = info["m"] or m or n
+        f = np.empty(m)
+        sys = None if sys is None else np.ascontiguousarray(sys, dtype=np.float64)
+        shared = None if shared is None else np.ascontiguousarray(shared, dtype=np.float64)
+        rc = self.lib.nlo_eval_fcn(fid, m, n, self._ptr(x), self._ptr(sys), self._ptr(shared), self._ptr(f))
+        if rc:
+            raise RuntimeError("nlo_eval_fcn -> %d" % rc)
+        return f
+
+    def jacobian(self, fcn, x, m=0, sys=None, shared=None, params=None):
+        fid = self.fcn_id(fcn) if isinstance(fcn, str) else fcn
+        info = self.fcn_info(fid)
+        x = np.array(x, dtype=np.float64)
+        n = info["n"] or x.size
+        m = info["m"] or m or n
+        jac = np.empty((n, m))  # column-major m x n
+        p = params or self.params()
+        sys = None if sys is None else np.ascontiguousarray(sys, dtype=np.float64)
+        shared = None if shared is None else np.ascontiguousarray(shared, dtype=np.float64)
+        rc = self.lib.nlo_jacobian(fid, m, n, C.byref(p), self._ptr(x), self._ptr(sys), self._ptr(shared), self._ptr(jac))
+        if rc:
+            raise RuntimeError("nlo_jacobian -> %d" % rc)
+        return jac.T.copy()
+
+    def solve(self, solver, fcn, x0, m=0, sys=None, shared=None, params=None):
+        """One system. Returns (x, fvec, ib(dict), status)."""
+        fid = self.fcn_id(fcn) if isinstance(fcn, str) else fcn
+        info = self.fcn_info(fid)
+        x = np.array(x0, dtype=np.float64)
+        n = info["n"] or x.size
+        m = info["m"] or m or n
+        f = np.zeros(m)
+        ib = np.zeros(1, dtype=IB_DTYPE)
+        p = params or self.params()
+        sys = None if sys is None else np.ascontiguousarray(sys, dtype=np.float64)
+        shared = None if shared is None else np.ascontiguousarray(shared, dtype=np.float64)
+        st = self.lib.nlo_solve(SOLVERS[solver] if isinstance(solver, str) else solver, fid, m, n, C.byref(p),
+                                self._ptr(x), self._ptr(f), self._ptr(sys), self._ptr(shared), self._ptr(ib))
+        return x, f, {k: int(ib[0][k]) for k in IB_DTYPE.names}, st
+
+    def solve_batch(self, solver, fcn, x0, m=0, sys=None, shared=None, params=None, nthreads=0):
+        """x0: (n, B) SoA. Returns (x (n,B), fvec (m,B), ib (B,) structured, status (B,))."""
+        fid = self.fcn_id(fcn) if isinstance(fcn, str) else fcn
+        info = self.fcn_info(fid)
+        x = np.array(x0, dtype=np.float64, order="C")
+        n, B = x.shape
+        if info["n"] and info["n"] != n:
+            raise ValueError("n mismatch")
+        m = info["m"] or m or n
+        f = np.zeros((m, B))
+        ib = np.zeros(B, dtype=IB_DTYPE)
+        status = np.zeros(B, dtype=np.int32)
+        p = params or self.params()
+        sys = None if sys is None else np.ascontiguousarray(sys, dtype=np.float64)
+        shared = None if shared is None else np.ascontiguousarray(shared, dtype=np.float64)
+        rc = self.lib.nlo_solve_batch(SOLVERS[solver] if isinstance(solver, str) else solver, fid, C.c_long(B), m, n,
+                                      C.byref(p), self._ptr(x), self._ptr(f), self._ptr(sys), self._ptr(shared),
+                                      self._ptr(ib), self._ptr(status), int(nthreads))
+        if rc:
+            raise RuntimeError("nlo_solve_batch -> %d" % rc)
+        return x, f, ib, status

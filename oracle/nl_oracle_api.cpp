@@ -1,0 +1,196 @@
+// oracle/nl_oracle_api.cpp — TEST INFRASTRUCTURE ONLY.
+//
+// extern "C" surface of the CPU oracle, loaded with ctypes by tests/, by
+// __graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference legs.  The
+// product library (nonlin_b200/libnonlin_b200.so) never links or loads this file.
+//
+// Batch layout is the same SoA the engine's C ABI uses: x[j*B + b], fvec[i*B + b],
+// sys[k*B + b] (system index fastest — a Fortran array declared x(B, n)).
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "nl_lapack.h"
+#include "nl_solvers.h"
+
+namespace nlo {
+static int g_libm_exp = 0;
+void nl_set_libm_exp(int on) { g_libm_exp = on; }
+int nl_get_libm_exp() { return g_libm_exp; }
+#ifdef NL_COUNT_FLOPS
+thread_local unsigned long long g_flops = 0;
+#endif
+}  // namespace nlo
+
+using namespace nlo;
+
+static std::atomic<unsigned long long> g_flops_total{0};
+
+static inline real* R(double* p) { return reinterpret_cast<real*>(p); }
+static inline const real* R(const double* p) { return reinterpret_cast<const real*>(p); }
+
+static int resolve_sizes(const Problem* p, int* m, int* n, int* sys_len) {
+    if (!p) return NL_UNDEFINED_FUNCTION_ERROR;
+    if (p->m != 0) { if (*m != 0 && *m != p->m) return NL_ARRAY_SIZE_ERROR; *m = p->m; }
+    if (p->n != 0) { if (*n != 0 && *n != p->n) return NL_ARRAY_SIZE_ERROR; *n = p->n; }
+    if (p->id == NL_FCN_EXT_ROSENBROCK) { if (*m == 0) *m = *n; if (*m != *n || (*n & 1)) return NL_INVALID_INPUT_ERROR; }
+    if (*m <= 0 || *n <= 0) return NL_INVALID_INPUT_ERROR;
+    *sys_len = p->sys_len < 0 ? *m : p->sys_len;
+    return 0;
+}
+
+static int solve_one(int solver, const Problem* p, const FcnCtx* c, const Params* prm, real* x, real* fvec,
+                     IterBehavior* ib, Workspace* ws) {
+    switch (solver) {
+        case 0: return lm_solve(p, c, prm, x, fvec, ib, ws);
+        case 1: return newton_solve(p, c, prm, x, fvec, ib, ws);
+        case 2: return broyden_solve(p, c, prm, x, fvec, ib, ws);
+    }
+    return NL_INVALID_INPUT_ERROR;
+}
+
+extern "C" {
+
+int nlo_is_counting_build(void) {
+#ifdef NL_COUNT_FLOPS
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+unsigned long long nlo_flops_total(void) { return g_flops_total.load(); }
+void nlo_flops_reset(void) { g_flops_total.store(0); }
+
+void nlo_set_libm_exp(int on) { nl_set_libm_exp(on); }
+
+int nlo_fcn_lookup(const char* name) {
+    const Problem* p = nl_problem_by_name(name);
+    return p ? p->id : -1;
+}
+
+int nlo_fcn_info(int id, int* m, int* n, int* sys_len, int* shared_len, int* has_jac) {
+    const Problem* p = nl_problem(id);
+    if (!p) return -1;
+    *m = p->m; *n = p->n; *sys_len = p->sys_len; *shared_len = p->shared_len; *has_jac = p->jac != nullptr;
+    return 0;
+}
+
+void nlo_params_default(Params* p) { params_default(p); }
+
+double nlo_soft_exp(double x) { return soft_exp_d(x); }
+double nlo_norm2(const double* v, int n) { return dval(f_norm2(R(v), n)); }
+double nlo_dnrm2(const double* v, int n) { return dval(la_dnrm2(n, R(v), 1)); }
+
+int nlo_eval_fcn(int fcn_id, int m, int n, const double* x, const double* sys, const double* shared, double* f) {
+    const Problem* p = nl_problem(fcn_id);
+    int sl;
+    int rc = resolve_sizes(p, &m, &n, &sl);
+    if (rc) return rc;
+    FcnCtx c = {m, n, R(sys), R(shared)};
+    p->fcn(R(x), R(f), &c);
+    return 0;
+}
+
+// vecfcn_helper%jacobian without fv (reference computes f(x) itself, multi_eqn:257-259)
+int nlo_jacobian(int fcn_id, int m, int n, const Params* prm, double* x, const double* sys, const double* shared,
+                 double* jac) {
+    const Problem* p = nl_problem(fcn_id);
+    int sl;
+    int rc = resolve_sizes(p, &m, &n, &sl);
+    if (rc) return rc;
+    FcnCtx c = {m, n, R(sys), R(shared)};
+    std::vector<real> f(m), w(m);
+    p->fcn(R(x), f.data(), &c);
+    fd_jacobian(p, &c, prm, R(x), R(jac), f.data(), w.data());
+    return 0;
+}
+
+// pieces exposed for unit tests against scipy's LAPACK
+void nlo_dgeqr2_dorg2r(int n, const double* a, double* q, double* r) {
+    std::vector<real> tau(n), work(n);
+    for (long e = 0; e < (long)n * n; ++e) R(q)[e] = R(a)[e];
+    la_dgeqr2(n, n, R(q), n, tau.data(), work.data());
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i) R(r)[i + (long)j * n] = (i <= j) ? R(q)[i + (long)j * n] : real(0.0);
+    la_dorg2r(n, n, n, R(q), n, tau.data(), work.data());
+}
+void nlo_dqr1up(int n, double* q, double* r, const double* u, const double* v) {
+    std::vector<real> w(2 * n);
+    la_dqr1up(n, n, R(q), n, R(r), n, R(u), R(v), w.data());
+}
+int nlo_dgesv(int n, double* a, int* ipiv, double* b) {
+    int info = la_dgetrf(n, n, R(a), n, ipiv);
+    la_dgetrs(n, R(a), n, ipiv, R(b));
+    return info;
+}
+void nlo_lmfactor(int m, int n, double* a, int* ipvt, double* rdiag, double* acnorm) {
+    std::vector<real> wa(n);
+    lm_factor(m, n, R(a), true, ipvt, R(rdiag), R(acnorm), wa.data());
+}
+
+// one system, contiguous x(n), fvec(m), sys(sys_len)
+int nlo_solve(int solver, int fcn_id, int m, int n, const Params* prm, double* x, double* fvec, const double* sys,
+              const double* shared, IterBehavior* ib) {
+    const Problem* p = nl_problem(fcn_id);
+    int sl;
+    int rc = resolve_sizes(p, &m, &n, &sl);
+    if (rc) return rc;
+    FcnCtx c = {m, n, R(sys), R(shared)};
+    Workspace ws;
+#ifdef NL_COUNT_FLOPS
+    g_flops = 0;
+#endif
+    int st = solve_one(solver, p, &c, prm, R(x), R(fvec), ib, &ws);
+#ifdef NL_COUNT_FLOPS
+    g_flops_total += g_flops;
+#endif
+    return st;
+}
+
+// B systems, SoA; one system per OpenMP thread at a time (schedule(dynamic)), workspaces
+// allocated once per thread.  Returns 0 or an API-level error; per-system codes in status[].
+int nlo_solve_batch(int solver, int fcn_id, long B, int m, int n, const Params* prm, double* x, double* fvec,
+                    const double* sys, const double* shared, IterBehavior* ib, int32_t* status, int nthreads) {
+    const Problem* p = nl_problem(fcn_id);
+    int sl;
+    int rc = resolve_sizes(p, &m, &n, &sl);
+    if (rc) return rc;
+    if (solver < 0 || solver > 2) return NL_INVALID_INPUT_ERROR;
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+    nthreads = 1;
+#endif
+#pragma omp parallel num_threads(nthreads)
+    {
+        Workspace ws;
+        std::vector<real> xl(n), fl(m), sl_buf(sl > 0 ? sl : 1);
+#ifdef NL_COUNT_FLOPS
+        g_flops = 0;
+#endif
+#pragma omp for schedule(dynamic, 64)
+        for (long b = 0; b < B; ++b) {
+            for (int j = 0; j < n; ++j) xl[j] = R(x)[(long)j * B + b];
+            for (int k = 0; k < sl; ++k) sl_buf[k] = R(sys)[(long)k * B + b];
+            FcnCtx c = {m, n, sl > 0 ? sl_buf.data() : nullptr, R(shared)};
+            IterBehavior lib;
+            int st = solve_one(solver, p, &c, prm, xl.data(), fl.data(), &lib, &ws);
+            for (int j = 0; j < n; ++j) R(x)[(long)j * B + b] = xl[j];
+            for (int i = 0; i < m; ++i) R(fvec)[(long)i * B + b] = fl[i];
+            if (ib) ib[b] = lib;
+            if (status) status[b] = st;
+        }
+#ifdef NL_COUNT_FLOPS
+        g_flops_total += g_flops;
+#endif
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,169 @@
+/* nonlin_batch.h — C ABI of the B200 batched nonlinear-solver engine (libnonlin_b200.so).
+ *
+ * This is the drop-in boundary for the reference's "M equations / N unknowns" solver path.
+ * The reference (jchristopherson/nonlin, Fortran) exposes type-bound procedures that are not
+ * C-interoperable; a maintainer binds these entry points with iso_c_binding
+ * (fortran/nonlin_batch.f90) next to the same-named Fortran types.  Each
+ * entry point cites the reference interface it replaces (paths relative to the reference
+ * repository root).
+ *
+ * Batch layout: B independent systems, structure-of-arrays with the system index fastest:
+ *     x[j*B + b]    j = 0..n-1      (a Fortran array declared  x(B, n))
+ *     fvec[i*B + b] i = 0..m-1      (                          fvec(B, m))
+ *     sys[k*B + b]  k = 0..sys_len-1  per-system data of the residual (the `args` analogue)
+ *     shared[i]     data common to all systems (e.g. abscissae)
+ * Every data pointer may be a host pointer or a device pointer (detected with
+ * cudaPointerGetAttributes); host buffers (pageable or pinned) are copied to and from the handle's
+ * grow-only device workspace on the call's stream, and the call then synchronises that stream.
+ * There is no CPU fallback: every entry point that computes returns NLB_ERR_NO_DEVICE if no
+ * CUDA device is usable.
+ *
+ * Return value of every function: 0 or an NLB_ERR_* API-level error.  Algorithmic outcomes
+ * are per system: status[b] is 0 or the NL_* code the reference would have executed
+ * `error stop` with (src/nonlin_error_handling.f90:10-38); x, fvec and ib hold the state at
+ * that point, as the reference fills `ib` before stopping (src/nonlin_least_squares.f90:378-390).
+ */
+#ifndef NONLIN_BATCH_H
+#define NONLIN_BATCH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- per-system status codes: src/nonlin_error_handling.f90:10-38 ------------------- */
+#define NLB_NO_ERROR 0
+#define NLB_INVALID_INPUT_ERROR 201
+#define NLB_ARRAY_SIZE_ERROR 202
+/* NL_CONVERGENCE_ERROR aliases linalg's LA_CONVERGENCE_ERROR (linalg is not vendored in the
+ * reference tree; 106 is the value in linalg's published C header). */
+#define NLB_CONVERGENCE_ERROR 106
+#define NLB_DIVERGENT_BEHAVIOR_ERROR 206
+#define NLB_SPURIOUS_CONVERGENCE_ERROR 207
+#define NLB_TOLERANCE_TOO_SMALL_ERROR 208
+#define NLB_UNDEFINED_FUNCTION_ERROR 211
+#define NLB_UNDERDEFINED_PROBLEM_ERROR 212
+
+/* ---- API-level errors (function return values) -------------------------------------- */
+#define NLB_OK 0
+#define NLB_ERR_INVALID_ARGUMENT 1   /* null pointer, B < 0, bad handle                          */
+#define NLB_ERR_UNKNOWN_FCN 2        /* fcn id not registered  (ref: NL_UNDEFINED_FUNCTION_ERROR)  */
+#define NLB_ERR_SIZE 3               /* m/n do not match the registered residual, or m < n for LM,
+                                        or m != n for Newton / quasi-Newton
+                                        (ref: src/nonlin_least_squares.f90:189, src/nonlin_solve.f90:237,519) */
+#define NLB_ERR_UNSUPPORTED 4        /* no kernel instantiated for this (solver, fcn) pair         */
+#define NLB_ERR_CUDA 5               /* a CUDA runtime call failed: see nlb_last_error()           */
+#define NLB_ERR_NO_DEVICE 6          /* no usable CUDA device: the engine has no CPU fallback      */
+
+/* Solver settings = the private members behind the reference's getters/setters. */
+typedef struct nlb_params {
+    int32_t max_fcn_evals;        /* equation_solver%set_max_fcn_evals      default 100    src/nonlin_multi_eqn_mult_var.f90:69,313 */
+    double fcn_tol;               /* equation_solver%set_fcn_tolerance      default 1e-8   :71,334  */
+    double var_tol;               /* equation_solver%set_var_tolerance      default 1e-12  :73,354  */
+    double grad_tol;              /* equation_solver%set_gradient_tolerance default 1e-12  :75,375  */
+    double lm_factor;             /* least_squares_solver%set_step_scaling_factor, default 100, clamped to [0.1, 100]
+                                     src/nonlin_least_squares.f90:25,96-115 */
+    int32_t jacobian_interval;    /* quasi_newton_solver%set_jacobian_interval  default 5  src/nonlin_solve.f90:51,439 */
+    int32_t use_line_search;      /* line_search_solver%set_use_line_search     default 1  src/nonlin_solve.f90:30,144 */
+    int32_t ls_max_fcn_evals;     /* line_search%set_max_fcn_evals      default 100   src/nonlin_linesearch.f90:35,82  */
+    double ls_alpha;              /* line_search%set_scaling_factor     default 1e-4  src/nonlin_linesearch.f90:38,107 */
+    double ls_factor;             /* line_search%set_distance_factor    default 0.1, (0,1) else 0.1 / 0.99
+                                     src/nonlin_linesearch.f90:46,133-149 */
+    int32_t use_analytic_jacobian;/* vecfcn_helper%set_jacobian was called (registered Jacobian of the residual is
+                                     used instead of forward differences)  src/nonlin_multi_eqn_mult_var.f90:143,241 */
+    int32_t max_iter_guard;       /* not in the reference: bound on the quasi-Newton iteration counter, which the
+                                     reference can spin forever on uphill restarts (src/nonlin_solve.f90:330-337) */
+} nlb_params;
+
+/* iteration_behavior, src/nonlin_types.f90:8-29 (gfortran default LOGICAL = 4 bytes). */
+typedef struct nlb_iteration_behavior {
+    int32_t iter_count;
+    int32_t fcn_count;
+    int32_t jacobian_count;
+    int32_t gradient_count;
+    int32_t converge_on_fcn;
+    int32_t converge_on_chng;
+    int32_t converge_on_zero_diff;
+} nlb_iteration_behavior;
+
+/* Batch statistics (the one quantity that is reduced across GPUs). */
+enum {
+    NLB_STAT_SYSTEMS = 0,          /* systems solved                                   */
+    NLB_STAT_CONVERGED = 1,        /* status == 0                                      */
+    NLB_STAT_CONVERGED_FCN = 2,    /* converge_on_fcn                                  */
+    NLB_STAT_CONVERGED_CHNG = 3,   /* converge_on_chng                                 */
+    NLB_STAT_CONVERGED_ZERO_DIFF = 4,
+    NLB_STAT_FAILED = 5,           /* status != 0                                      */
+    NLB_STAT_SUM_ITER = 6,
+    NLB_STAT_SUM_FCN = 7,
+    NLB_STAT_SUM_JAC = 8,
+    NLB_STAT_MAX_ITER = 9,         /* combine across ranks with MAX, the others with SUM */
+    NLB_STAT_COUNT = 16
+};
+
+typedef struct nlb_handle nlb_handle;
+
+/* Engine handle: owns a stream and the device staging workspace; one per GPU, thread-safe
+ * per handle.  Replaces the per-solve allocate/deallocate of the reference
+ * (src/nonlin_least_squares.f90:199-208, src/nonlin_solve.f90:247-254,529-534). */
+int nlb_create(nlb_handle** handle, int device);
+int nlb_destroy(nlb_handle* handle);
+const char* nlb_last_error(const nlb_handle* handle);
+/* number of engine kernels launched through this handle since creation */
+int64_t nlb_kernel_launch_count(const nlb_handle* handle);
+
+/* Defaults of the reference's solver objects (file:line in nlb_params above). */
+void nlb_params_default(nlb_params* p);
+
+/* Residual registry: the analogue of vecfcn_helper%set_fcn(fcn, nfcn, nvar)
+ * (src/nonlin_multi_eqn_mult_var.f90:126-140) for compiled-in __device__ residuals.
+ * m or n reported as 0 mean "taken from the call"; sys_len / shared_len of -1 mean m. */
+int nlb_vecfcn_count(void);
+int nlb_vecfcn_lookup(const char* name);            /* id or -1 */
+const char* nlb_vecfcn_name(int fcn_id);            /* NULL if unknown */
+int nlb_vecfcn_info(int fcn_id, int* m, int* n, int* sys_len, int* shared_len, int* has_jacobian);
+
+/* least_squares_solver%solve  (lss_solve, src/nonlin_least_squares.f90:118-391) over B systems.
+ * x in/out, fvec out, ib / status out (either may be NULL). stream: cudaStream_t, or NULL for the
+ * handle's own stream (pass cudaStreamLegacy to name the legacy default stream).  Asynchronous when every pointer is a device pointer; synchronous otherwise. */
+int nlb_least_squares_solve_batch(nlb_handle* handle, const nlb_params* params, int fcn_id, int64_t B, int m, int n,
+                                  double* x, double* fvec, const double* sys, const double* shared,
+                                  nlb_iteration_behavior* ib, int32_t* status, void* stream);
+
+/* newton_solver%solve  (ns_solve, src/nonlin_solve.f90:452-638) over B systems. */
+int nlb_newton_solve_batch(nlb_handle* handle, const nlb_params* params, int fcn_id, int64_t B, int m, int n,
+                           double* x, double* fvec, const double* sys, const double* shared,
+                           nlb_iteration_behavior* ib, int32_t* status, void* stream);
+
+/* quasi_newton_solver%solve  (qns_solve, src/nonlin_solve.f90:156-425) over B systems. */
+int nlb_quasi_newton_solve_batch(nlb_handle* handle, const nlb_params* params, int fcn_id, int64_t B, int m, int n,
+                                 double* x, double* fvec, const double* sys, const double* shared,
+                                 nlb_iteration_behavior* ib, int32_t* status, void* stream);
+
+/* vecfcn_helper%fcn  (vfh_fcn, src/nonlin_multi_eqn_mult_var.f90:178-195) over B points. */
+int nlb_vecfcn_eval_batch(nlb_handle* handle, int fcn_id, int64_t B, int m, int n, const double* x, double* fvec,
+                          const double* sys, const double* shared, void* stream);
+
+/* vecfcn_helper%jacobian  (vfh_jac_fcn, src/nonlin_multi_eqn_mult_var.f90:198-277) over B points:
+ * forward differences, or the registered Jacobian when params->use_analytic_jacobian.
+ * jac[(i + j*m)*B + b] = d f_i / d x_j of system b (column-major m x n per system). */
+int nlb_jacobian_batch(nlb_handle* handle, const nlb_params* params, int fcn_id, int64_t B, int m, int n,
+                       const double* x, double* jac, const double* sys, const double* shared, void* stream);
+
+/* Convergence statistics of a finished batch: stats[NLB_STAT_COUNT] (host or device pointer).
+ * Multi-GPU runs sum these across ranks (MAX for NLB_STAT_MAX_ITER) — the only collective of
+ * the path. */
+int nlb_reduce_stats(nlb_handle* handle, int64_t B, const nlb_iteration_behavior* ib, const int32_t* status,
+                     int64_t* stats, void* stream);
+
+/* Measured FP64 throughput of this GPU (roofline denominator): dependent-chain-free DFMA and
+ * DADD/DMUL micro-kernels, TFLOP/s.  The parity build issues no DFMA, so its ceiling is the
+ * second number. */
+int nlb_measure_fp64_peak(nlb_handle* handle, double* dfma_tflops, double* dadd_dmul_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NONLIN_BATCH_H */

@@ -1,0 +1,484 @@
+"""Host-side mirror of the reference's solver interface for the batched hot path.
+
+Same type names, setters and argument meaning as jchristopherson/nonlin (Appendix C of
+SURVEY.md), with a batch `solve` that forwards to the C ABI in include/nonlin_batch.h:
+
+    reference (Fortran)                               here
+    -----------------------------------------------   -------------------------------------------
+    type(vecfcn_helper) :: obj                        obj = vecfcn_helper()
+    call obj%set_fcn(fcn, m, n)                       obj.set_fcn("misc_2fcn", m, n)   # registered name
+    call obj%set_jacobian(jac)                        obj.set_jacobian()               # registered Jacobian
+    type(quasi_newton_solver) :: solver               solver = quasi_newton_solver()
+    call solver%set_fcn_tolerance(1d-8) ...           solver.set_fcn_tolerance(1e-8) ...
+    call solver%solve(obj, x, f, ib, args)            status = solver.solve(obj, x, f, ib, args=...)
+
+`x` is (n, B), `f` is (m, B), args is (sys_len, B): system index fastest (a Fortran x(B, n)).
+Arrays are numpy (host; staged by the engine) or torch CUDA tensors (used in place,
+asynchronously on torch's current stream).  Where the reference executes `error stop code`,
+the per-system `status[b]` holds that code instead.
+
+This module contains no numerical code: everything is computed by libnonlin_b200.so on the GPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import IB_DTYPE, NLB_STAT_COUNT, NLB_STAT_NAMES, nlb_params
+
+_LIB = _lib.load()
+
+
+class NonlinError(RuntimeError):
+    """API-level failure (bad sizes, unknown residual, CUDA error, no device)."""
+
+    def __init__(self, code, msg):
+        super().__init__("nonlin_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+# ---------------------------------------------------------------------------------------------
+# engine handle (one per GPU)
+# ---------------------------------------------------------------------------------------------
+class Engine:
+    """Owns an nlb_handle (stream + staging workspace) on one device."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = _LIB.nlb_create(C.byref(self._h), int(device))
+        if rc != _lib.NLB_OK:
+            self._h = None
+            raise NonlinError(rc, "nlb_create(device=%d) failed (no usable CUDA device? the engine has no CPU fallback)" % device)
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _LIB.nlb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != _lib.NLB_OK:
+            raise NonlinError(rc, _LIB.nlb_last_error(self._h).decode())
+
+    @property
+    def kernel_launches(self):
+        return int(_LIB.nlb_kernel_launch_count(self._h))
+
+    def measure_fp64_peak(self):
+        a, b = C.c_double(), C.c_double()
+        self.check(_LIB.nlb_measure_fp64_peak(self._h, C.byref(a), C.byref(b)))
+        return {"dfma_tflops": a.value, "dadd_dmul_tflops": b.value}
+
+    def reduce_stats(self, ib, status, B=None):
+        """Batch convergence statistics -> dict (host)."""
+        out = np.zeros(NLB_STAT_COUNT, dtype=np.int64)
+        B = int(B if B is not None else _length(status if status is not None else ib))
+        self.check(_LIB.nlb_reduce_stats(self._h, B, _ptr(ib), _ptr(status), _ptr(out), _stream_of(ib, status)))
+        return {k: int(out[i]) for i, k in enumerate(NLB_STAT_NAMES)}
+
+    def reduce_stats_device(self, ib, status, out, B):
+        """Same, into a device int64[16] tensor, asynchronously (for the NCCL all-reduce)."""
+        self.check(_LIB.nlb_reduce_stats(self._h, int(B), _ptr(ib), _ptr(status), _ptr(out), _stream_of(ib, status, out)))
+
+
+_default_engines = {}
+
+
+def default_engine(device=0):
+    e = _default_engines.get(device)
+    if e is None:
+        e = _default_engines[device] = Engine(device)
+    return e
+
+
+# ---------------------------------------------------------------------------------------------
+# pointer plumbing: numpy arrays and torch tensors
+# ---------------------------------------------------------------------------------------------
+def _is_torch(a):
+    return type(a).__module__.startswith("torch")
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if _is_torch(a):
+        if not a.is_contiguous():
+            raise ValueError("tensors passed to the engine must be contiguous")
+        return C.c_void_p(a.data_ptr())
+    if not a.flags["C_CONTIGUOUS"]:
+        raise ValueError("arrays passed to the engine must be C-contiguous")
+    return C.c_void_p(a.ctypes.data)
+
+
+def _length(a):
+    return a.shape[0]
+
+
+def _stream_of(*arrays):
+    for a in arrays:
+        if a is not None and _is_torch(a) and a.is_cuda:
+            import torch
+
+            # torch's default stream is the legacy NULL stream; NULL means "the handle's own stream" in
+            # the C ABI, so name it explicitly (cudaStreamLegacy == (cudaStream_t)0x1)
+            return C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream or 1)
+    return None
+
+
+def _device_of(*arrays):
+    for a in arrays:
+        if a is not None and _is_torch(a) and a.is_cuda:
+            return a.device.index or 0
+    return None
+
+
+def _check_f64(name, a, shape):
+    if _is_torch(a):
+        import torch
+
+        ok = a.dtype == torch.float64
+    else:
+        ok = a.dtype == np.float64
+    if not ok:
+        raise TypeError("%s must be float64" % name)
+    if tuple(a.shape) != tuple(shape):
+        # mirrors the reference's size checks (`error stop flag`, src/nonlin_least_squares.f90:190-196)
+        raise NonlinError(_lib.NLB_ERR_SIZE, "%s has shape %s, expected %s" % (name, tuple(a.shape), tuple(shape)))
+
+
+# ---------------------------------------------------------------------------------------------
+# reference types
+# ---------------------------------------------------------------------------------------------
+def iteration_behavior(B, like=None):
+    """Array of B `iteration_behavior` records (reference src/nonlin_types.f90:8-29)."""
+    if like is not None and _is_torch(like) and like.is_cuda:
+        import torch
+
+        return torch.zeros((B, 7), dtype=torch.int32, device=like.device)
+    return np.zeros(B, dtype=IB_DTYPE)
+
+
+def ib_view(ib):
+    """Structured numpy view of an iteration_behavior array (copies a CUDA tensor to host)."""
+    if _is_torch(ib):
+        return ib.detach().cpu().numpy().view(IB_DTYPE).reshape(-1)
+    return ib
+
+
+class vecfcn_helper:
+    """Problem definition (reference src/nonlin_multi_eqn_mult_var.f90:41-65).
+
+    set_fcn takes the *name* of a registered __device__ residual instead of a procedure
+    pointer; set_jacobian() selects its registered analytic Jacobian (the reference's
+    vfh_set_jac), otherwise forward differences are used (vfh_jac_fcn :244-276).
+    """
+
+    def __init__(self):
+        self._fcn_id = -1
+        self._m = 0
+        self._n = 0
+        self._use_jac = False
+        self._shared = None
+        self._info = None
+
+    def set_fcn(self, fcn, nfcn=0, nvar=0):
+        fid = _LIB.nlb_vecfcn_lookup(fcn.encode()) if isinstance(fcn, str) else int(fcn)
+        vals = [C.c_int() for _ in range(5)]
+        if fid < 0 or _LIB.nlb_vecfcn_info(fid, *[C.byref(v) for v in vals]) != 0:
+            raise NonlinError(_lib.NLB_ERR_UNKNOWN_FCN, "residual %r is not registered" % (fcn,))
+        m, n, sys_len, shared_len, has_jac = [v.value for v in vals]
+        if (m and nfcn and m != nfcn) or (n and nvar and n != nvar):
+            raise NonlinError(_lib.NLB_ERR_SIZE, "%r is registered as %dx%d, not %dx%d" % (fcn, m, n, nfcn, nvar))
+        self._fcn_id = fid
+        self._m = m or int(nfcn)
+        self._n = n or int(nvar)
+        if fid == _LIB.nlb_vecfcn_lookup(b"ext_rosenbrock") and not self._m:
+            self._m = self._n
+        if self._m <= 0 or self._n <= 0:
+            raise NonlinError(_lib.NLB_ERR_SIZE, "this residual family needs explicit nfcn / nvar")
+        self._info = {
+            "sys_len": self._m if sys_len < 0 else sys_len,
+            "shared_len": self._m if shared_len < 0 else shared_len,
+            "has_jac": bool(has_jac),
+        }
+        self._use_jac = False
+
+    def set_jacobian(self, enable=True):
+        if enable and not (self._info and self._info["has_jac"]):
+            raise NonlinError(_lib.NLB_ERR_UNSUPPORTED, "no analytic Jacobian is registered for this residual")
+        self._use_jac = bool(enable)
+
+    def set_shared_data(self, shared):
+        """Data every system of the batch sees (e.g. the abscissae of a curve fit)."""
+        self._shared = shared
+
+    def is_fcn_defined(self):
+        return self._fcn_id >= 0
+
+    def is_jacobian_defined(self):
+        return self._use_jac
+
+    def get_equation_count(self):
+        return self._m
+
+    def get_variable_count(self):
+        return self._n
+
+    # vecfcn_helper%fcn over a batch
+    def fcn(self, x, f=None, args=None, engine=None):
+        eng = engine or default_engine(_device_of(x, f, args) or 0)
+        B = x.shape[1]
+        _check_f64("x", x, (self._n, B))
+        if f is None:
+            f = _empty_like(x, (self._m, B))
+        _check_f64("f", f, (self._m, B))
+        eng.check(_LIB.nlb_vecfcn_eval_batch(eng._h, self._fcn_id, B, self._m, self._n, _ptr(x), _ptr(f), _ptr(args),
+                                             _ptr(self._shared), _stream_of(x, f, args)))
+        return f
+
+    # vecfcn_helper%jacobian over a batch: (n, m, B) = column-major m x n per system
+    def jacobian(self, x, jac=None, args=None, engine=None):
+        eng = engine or default_engine(_device_of(x, jac, args) or 0)
+        B = x.shape[1]
+        _check_f64("x", x, (self._n, B))
+        if jac is None:
+            jac = _empty_like(x, (self._n, self._m, B))
+        _check_f64("jac", jac, (self._n, self._m, B))
+        p = nlb_params()
+        _LIB.nlb_params_default(C.byref(p))
+        p.use_analytic_jacobian = int(self._use_jac)
+        eng.check(_LIB.nlb_jacobian_batch(eng._h, C.byref(p), self._fcn_id, B, self._m, self._n, _ptr(x), _ptr(jac),
+                                          _ptr(args), _ptr(self._shared), _stream_of(x, jac, args)))
+        return jac
+
+
+def _empty_like(a, shape):
+    if _is_torch(a):
+        import torch
+
+        return torch.empty(shape, dtype=torch.float64, device=a.device)
+    return np.empty(shape, dtype=np.float64)
+
+
+class line_search:
+    """Backtracking line-search settings (reference src/nonlin_linesearch.f90:18-65)."""
+
+    def __init__(self):
+        self._max_eval = 100
+        self._alpha = 1.0e-4
+        self._factor = 0.1
+
+    def get_max_fcn_evals(self):
+        return self._max_eval
+
+    def set_max_fcn_evals(self, x):
+        self._max_eval = int(x)
+
+    def get_scaling_factor(self):
+        return self._alpha
+
+    def set_scaling_factor(self, x):
+        self._alpha = float(x)
+
+    def get_distance_factor(self):
+        return self._factor
+
+    def set_distance_factor(self, x):
+        # src/nonlin_linesearch.f90:142-148
+        x = float(x)
+        if x <= 0.0:
+            self._factor = 0.1
+        elif x >= 1.0:
+            self._factor = 0.99
+        else:
+            self._factor = x
+
+
+class equation_solver:
+    """Base class with the tolerances (reference src/nonlin_multi_eqn_mult_var.f90:67-91)."""
+
+    _entry = None
+
+    def __init__(self, engine=None):
+        self._engine = engine
+        self._max_eval = 100
+        self._fcn_tol = 1.0e-8
+        self._xtol = 1.0e-12
+        self._gtol = 1.0e-12
+        self._print_status = False
+
+    def get_max_fcn_evals(self):
+        return self._max_eval
+
+    def set_max_fcn_evals(self, n):
+        self._max_eval = int(n)
+
+    def get_fcn_tolerance(self):
+        return self._fcn_tol
+
+    def set_fcn_tolerance(self, x):
+        self._fcn_tol = float(x)
+
+    def get_var_tolerance(self):
+        return self._xtol
+
+    def set_var_tolerance(self, x):
+        self._xtol = float(x)
+
+    def get_gradient_tolerance(self):
+        return self._gtol
+
+    def set_gradient_tolerance(self, x):
+        self._gtol = float(x)
+
+    def get_print_status(self):
+        return self._print_status
+
+    def set_print_status(self, x):
+        # Per-iteration printing needs a host round trip per step; the batch engine keeps every
+        # iteration on the device, so the flag is stored but nothing is printed.
+        self._print_status = bool(x)
+
+    def _params(self, fcn):
+        p = nlb_params()
+        _LIB.nlb_params_default(C.byref(p))
+        p.max_fcn_evals = self._max_eval
+        p.fcn_tol = self._fcn_tol
+        p.var_tol = self._xtol
+        p.grad_tol = self._gtol
+        p.use_analytic_jacobian = int(fcn.is_jacobian_defined())
+        return p
+
+    def solve(self, fcn, x, fvec=None, ib=None, args=None, status=None):
+        """Solve the B systems in x (n, B) in place. Returns the per-system status array.
+
+        Mirrors `call solver%solve(fcn, x, fvec, ib, args)` (nonlin_solver interface,
+        src/nonlin_multi_eqn_mult_var.f90:94-119).
+        """
+        if not fcn.is_fcn_defined():
+            raise NonlinError(_lib.NLB_ERR_UNKNOWN_FCN, "no residual set (NL_UNDEFINED_FUNCTION_ERROR)")
+        m, n = fcn.get_equation_count(), fcn.get_variable_count()
+        if x.ndim != 2:
+            raise NonlinError(_lib.NLB_ERR_SIZE, "x must be (n, B)")
+        B = x.shape[1]
+        _check_f64("x", x, (n, B))
+        if fvec is None:
+            fvec = _empty_like(x, (m, B))
+        _check_f64("fvec", fvec, (m, B))
+        if args is not None:
+            _check_f64("args", args, (fcn._info["sys_len"], B))
+        if status is None:
+            if _is_torch(x) and x.is_cuda:
+                import torch
+
+                status = torch.zeros(B, dtype=torch.int32, device=x.device)
+            else:
+                status = np.zeros(B, dtype=np.int32)
+        eng = self._engine or default_engine(_device_of(x, fvec, args, ib, status) or 0)
+        p = self._params(fcn)
+        entry = getattr(_LIB, self._entry)
+        eng.check(entry(eng._h, C.byref(p), fcn._fcn_id, B, m, n, _ptr(x), _ptr(fvec), _ptr(args), _ptr(fcn._shared),
+                        _ptr(ib), _ptr(status), _stream_of(x, fvec, args, ib, status)))
+        self.last_fvec = fvec
+        return status
+
+
+class least_squares_solver(equation_solver):
+    """Levenberg-Marquardt (reference src/nonlin_least_squares.f90:20-31, lss_solve :118-391)."""
+
+    _entry = "nlb_least_squares_solve_batch"
+
+    def __init__(self, engine=None):
+        super().__init__(engine)
+        self._factor = 100.0
+
+    def get_step_scaling_factor(self):
+        return self._factor
+
+    def set_step_scaling_factor(self, x):
+        # clamp to [0.1, 100], src/nonlin_least_squares.f90:108-114
+        x = float(x)
+        self._factor = 0.1 if x < 0.1 else (100.0 if x > 100.0 else x)
+
+    def _params(self, fcn):
+        p = super()._params(fcn)
+        p.lm_factor = self._factor
+        return p
+
+
+class line_search_solver(equation_solver):
+    """Base of the line-searched solvers (reference src/nonlin_solve.f90:20-41)."""
+
+    def __init__(self, engine=None):
+        super().__init__(engine)
+        self._line_search = None
+        self._use_line_search = True
+
+    def get_line_search(self):
+        return self._line_search
+
+    def set_line_search(self, ls):
+        c = line_search()
+        c._max_eval, c._alpha, c._factor = ls._max_eval, ls._alpha, ls._factor
+        self._line_search = c
+
+    def set_default_line_search(self):
+        self.set_line_search(line_search())
+
+    def is_line_search_defined(self):
+        return self._line_search is not None
+
+    def get_use_line_search(self):
+        return self._use_line_search
+
+    def set_use_line_search(self, x):
+        self._use_line_search = bool(x)
+
+    def _params(self, fcn):
+        p = super()._params(fcn)
+        p.use_line_search = int(self._use_line_search)
+        # the reference lazily installs a default line search inside solve (src/nonlin_solve.f90:229-233)
+        if self._use_line_search and self._line_search is None:
+            self.set_default_line_search()
+        if self._line_search is not None:
+            p.ls_max_fcn_evals = self._line_search._max_eval
+            p.ls_alpha = self._line_search._alpha
+            p.ls_factor = self._line_search._factor
+        return p
+
+
+class quasi_newton_solver(line_search_solver):
+    """Broyden's method with QR rank-1 updates (reference src/nonlin_solve.f90:43-58, qns_solve :156-425)."""
+
+    _entry = "nlb_quasi_newton_solve_batch"
+
+    def __init__(self, engine=None):
+        super().__init__(engine)
+        self._jdelta = 5
+
+    def get_jacobian_interval(self):
+        return self._jdelta
+
+    def set_jacobian_interval(self, n):
+        self._jdelta = int(n)
+
+    def _params(self, fcn):
+        p = super()._params(fcn)
+        p.jacobian_interval = self._jdelta
+        return p
+
+
+class newton_solver(line_search_solver):
+    """Newton's method with LU (reference src/nonlin_solve.f90:60-67, ns_solve :452-638)."""
+
+    _entry = "nlb_newton_solve_batch"
+
+
+def vecfcn_names():
+    return [_LIB.nlb_vecfcn_name(i).decode() for i in range(_LIB.nlb_vecfcn_count())]

@@ -1,0 +1,596 @@
+// nlb_api.cu — the C ABI of the engine (include/nonlin_batch.h): handle, residual registry,
+// launchers for the batch solvers, batch statistics and the FP64 peak probe.
+//
+// Compiled for sm_100a only, with -fmad=false (see nlb_math.cuh).  There is no CPU path in
+// this library: without a CUDA device every computing entry point fails with
+// NLB_ERR_NO_DEVICE.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "coop_kernels.cuh"
+#include "tps_lm.cuh"
+#include "tps_newton_broyden.cuh"
+
+using namespace nlb;
+
+// ---------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------
+struct nlb_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+    int64_t launches = 0;
+    // grow-only device staging for host-resident arguments
+    static constexpr int NSLOT = 8;
+    void* dbuf[NSLOT] = {nullptr};
+    size_t dcap[NSLOT] = {0};
+    int64_t* dstats = nullptr;
+    std::mutex mu;
+};
+
+namespace {
+
+enum Solver { SOLVER_LM = 0, SOLVER_NEWTON = 1, SOLVER_BROYDEN = 2 };
+
+int set_err(nlb_handle* h, int code, const char* what, cudaError_t ce = cudaSuccess) {
+    if (h) {
+        h->last_error = what;
+        if (ce != cudaSuccess) {
+            h->last_error += ": ";
+            h->last_error += cudaGetErrorString(ce);
+        }
+    }
+    return code;
+}
+
+#define NLB_CUDA(h, call)                                                   \
+    do {                                                                    \
+        cudaError_t _e = (call);                                            \
+        if (_e != cudaSuccess) return set_err((h), NLB_ERR_CUDA, #call, _e); \
+    } while (0)
+
+bool is_device_ptr(const void* p) {
+    if (!p) return true;
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// One argument of a call: the caller's pointer and the device pointer the kernel uses.
+struct Staged {
+    void* user = nullptr;
+    void* dev = nullptr;
+    size_t bytes = 0;
+    bool staged = false;
+};
+
+int stage_in(nlb_handle* h, int slot, const void* user, size_t bytes, bool copy_in, cudaStream_t s, Staged* out) {
+    out->user = const_cast<void*>(user);
+    out->bytes = bytes;
+    if (!user || bytes == 0) { out->dev = const_cast<void*>(user); return NLB_OK; }
+    if (is_device_ptr(user)) { out->dev = const_cast<void*>(user); return NLB_OK; }
+    if (h->dcap[slot] < bytes) {
+        if (h->dbuf[slot]) NLB_CUDA(h, cudaFree(h->dbuf[slot]));
+        h->dbuf[slot] = nullptr;
+        h->dcap[slot] = 0;
+        NLB_CUDA(h, cudaMalloc(&h->dbuf[slot], bytes));
+        h->dcap[slot] = bytes;
+    }
+    out->dev = h->dbuf[slot];
+    out->staged = true;
+    if (copy_in) NLB_CUDA(h, cudaMemcpyAsync(out->dev, user, bytes, cudaMemcpyHostToDevice, s));
+    return NLB_OK;
+}
+
+int stage_out(nlb_handle* h, const Staged& a, cudaStream_t s) {
+    if (a.staged && a.user) NLB_CUDA(h, cudaMemcpyAsync(a.user, a.dev, a.bytes, cudaMemcpyDeviceToHost, s));
+    return NLB_OK;
+}
+
+DevParams to_dev(const nlb_params* p) {
+    DevParams d;
+    d.max_fcn_evals = p->max_fcn_evals;
+    d.fcn_tol = p->fcn_tol;
+    d.var_tol = p->var_tol;
+    d.grad_tol = p->grad_tol;
+    d.lm_factor = p->lm_factor;
+    d.jacobian_interval = p->jacobian_interval;
+    d.use_line_search = p->use_line_search;
+    d.ls_max_fcn_evals = p->ls_max_fcn_evals;
+    d.ls_alpha = p->ls_alpha;
+    d.ls_factor = p->ls_factor;
+    d.use_analytic_jacobian = p->use_analytic_jacobian;
+    d.max_iter_guard = p->max_iter_guard;
+    return d;
+}
+
+// ---------------------------------------------------------------------------------------
+// thread-per-system kernels
+// ---------------------------------------------------------------------------------------
+constexpr int TPS_BLOCK = 128;
+
+template <class F, int SOLVER>
+__global__ void __launch_bounds__(TPS_BLOCK)
+tps_solve_kernel(DevParams p, long long B, double* __restrict__ x, double* __restrict__ fvec,
+                 const double* __restrict__ sys, const double* __restrict__ shared,
+                 nlb_iteration_behavior* __restrict__ ib, int32_t* __restrict__ status) {
+    constexpr int M = F::M, N = F::N;
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double xl[N], fl[M];
+#pragma unroll
+    for (int j = 0; j < N; ++j) xl[j] = x[j * B + b];
+    SysCtx c{sys ? sys + b : nullptr, shared, B, M, N};
+    SolveStats st;
+    if constexpr (SOLVER == SOLVER_LM) tps_lm_solve<F>(p, c, xl, fl, st);
+    else if constexpr (SOLVER == SOLVER_NEWTON) tps_newton_solve<F>(p, c, xl, fl, st);
+    else tps_broyden_solve<F>(p, c, xl, fl, st);
+#pragma unroll
+    for (int j = 0; j < N; ++j) x[j * B + b] = xl[j];
+#pragma unroll(M <= 8 ? M : 1)
+    for (int i = 0; i < M; ++i) fvec[i * B + b] = fl[i];
+    if (ib) {
+        nlb_iteration_behavior o;
+        o.iter_count = st.iter;
+        o.fcn_count = st.nfev;
+        o.jacobian_count = st.njac;
+        o.gradient_count = 0;
+        o.converge_on_fcn = st.cf;
+        o.converge_on_chng = st.cx;
+        o.converge_on_zero_diff = st.cg;
+        ib[b] = o;
+    }
+    if (status) status[b] = st.status;
+}
+
+template <class F>
+__global__ void __launch_bounds__(TPS_BLOCK)
+tps_eval_kernel(long long B, const double* __restrict__ x, double* __restrict__ fvec,
+                const double* __restrict__ sys, const double* __restrict__ shared) {
+    constexpr int M = F::M, N = F::N;
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double xl[N], fl[M];
+#pragma unroll
+    for (int j = 0; j < N; ++j) xl[j] = x[j * B + b];
+    SysCtx c{sys ? sys + b : nullptr, shared, B, M, N};
+    F::eval(xl, fl, c);
+#pragma unroll(M <= 8 ? M : 1)
+    for (int i = 0; i < M; ++i) fvec[i * B + b] = fl[i];
+}
+
+template <class F>
+__global__ void __launch_bounds__(TPS_BLOCK)
+tps_jacobian_kernel(int analytic, long long B, const double* __restrict__ x, double* __restrict__ jac,
+                    const double* __restrict__ sys, const double* __restrict__ shared) {
+    constexpr int M = F::M, N = F::N;
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double xl[N], fl[M], wrk[M], jl[M * N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) xl[j] = x[j * B + b];
+    SysCtx c{sys ? sys + b : nullptr, shared, B, M, N};
+    F::eval(xl, fl, c);                      // fv not supplied: evaluate f(x) first (multi_eqn:257-259)
+    fd_jacobian<F>(xl, jl, fl, wrk, c, analytic != 0);
+#pragma unroll(M * N <= 16 ? M * N : 1)
+    for (int e = 0; e < M * N; ++e) jac[e * B + b] = jl[e];
+}
+
+// ---------------------------------------------------------------------------------------
+// batch statistics
+// ---------------------------------------------------------------------------------------
+__global__ void stats_kernel(long long B, const nlb_iteration_behavior* __restrict__ ib,
+                             const int32_t* __restrict__ status, unsigned long long* __restrict__ out) {
+    unsigned long long v[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+        const int st = status ? status[b] : 0;
+        v[NLB_STAT_SYSTEMS] += 1;
+        v[NLB_STAT_CONVERGED] += (st == 0);
+        v[NLB_STAT_FAILED] += (st != 0);
+        if (ib) {
+            const nlb_iteration_behavior o = ib[b];
+            v[NLB_STAT_CONVERGED_FCN] += (o.converge_on_fcn != 0);
+            v[NLB_STAT_CONVERGED_CHNG] += (o.converge_on_chng != 0);
+            v[NLB_STAT_CONVERGED_ZERO_DIFF] += (o.converge_on_zero_diff != 0);
+            v[NLB_STAT_SUM_ITER] += (unsigned long long)o.iter_count;
+            v[NLB_STAT_SUM_FCN] += (unsigned long long)o.fcn_count;
+            v[NLB_STAT_SUM_JAC] += (unsigned long long)o.jacobian_count;
+            v[NLB_STAT_MAX_ITER] = max(v[NLB_STAT_MAX_ITER], (unsigned long long)o.iter_count);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+        unsigned long long s = v[k];
+        if (k == NLB_STAT_MAX_ITER) {
+            for (int off = 16; off > 0; off >>= 1) s = max(s, __shfl_down_sync(0xffffffffu, s, off));
+            if ((threadIdx.x & 31) == 0) atomicMax(&out[k], s);
+        } else {
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+            if ((threadIdx.x & 31) == 0 && s) atomicAdd(&out[k], s);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// FP64 peak probe: 8 independent chains per thread, no memory traffic in the loop
+// ---------------------------------------------------------------------------------------
+template <bool FMA>
+__global__ void fp64_peak_kernel(double* out, int iters, double seed) {
+    double a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = seed + k + threadIdx.x * 1e-9;
+    const double m = 1.0000000001, c = 1e-12;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (FMA) a[k] = __fma_rn(a[k], m, c);
+            else { a[k] = __dmul_rn(a[k], m); a[k] = __dadd_rn(a[k], c); }
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += a[k];
+    if (s == 12345.6789) out[0] = s;   // never true; keeps the chains alive
+}
+
+// ---------------------------------------------------------------------------------------
+// dispatch
+// ---------------------------------------------------------------------------------------
+template <class F, int SOLVER>
+int launch_tps_solve(nlb_handle* h, const DevParams& p, long long B, double* x, double* fvec, const double* sys,
+                     const double* shared, nlb_iteration_behavior* ib, int32_t* status, cudaStream_t s) {
+    if (B == 0) return NLB_OK;
+    const unsigned grid = (unsigned)((B + TPS_BLOCK - 1) / TPS_BLOCK);
+    tps_solve_kernel<F, SOLVER><<<grid, TPS_BLOCK, 0, s>>>(p, B, x, fvec, sys, shared, ib, status);
+    ++h->launches;
+    NLB_CUDA(h, cudaGetLastError());
+    return NLB_OK;
+}
+
+#define NLB_SQUARE_FCNS(X) \
+    X(Misc2Fcn) X(Misc2FcnA) X(PoorlyScaled2Fcn) X(PowellBadlyScaled) X(Misc2Fcn01) X(Polar) X(PolarScaled)
+#define NLB_FIXED_FCNS(X) NLB_SQUARE_FCNS(X) X(LsqPolyFit)
+
+template <int SOLVER>
+int dispatch_tps(nlb_handle* h, int fcn_id, const DevParams& p, long long B, double* x, double* fvec,
+                 const double* sys, const double* shared, nlb_iteration_behavior* ib, int32_t* status,
+                 cudaStream_t s) {
+    switch (fcn_id) {
+#define X(F) \
+    case F::ID: return launch_tps_solve<F, SOLVER>(h, p, B, x, fvec, sys, shared, ib, status, s);
+        NLB_SQUARE_FCNS(X)
+#undef X
+        case LsqPolyFit::ID:
+            if constexpr (SOLVER == SOLVER_LM)
+                return launch_tps_solve<LsqPolyFit, SOLVER_LM>(h, p, B, x, fvec, sys, shared, ib, status, s);
+            else
+                return set_err(h, NLB_ERR_SIZE, "Newton / quasi-Newton need m == n");
+        default: return set_err(h, NLB_ERR_UNSUPPORTED, "no thread-per-system kernel for this residual");
+    }
+}
+
+int check_sizes(nlb_handle* h, int fcn_id, int* m, int* n, int* sys_len, int* shared_len) {
+    if (fcn_id < 0 || fcn_id >= FCN_COUNT) return set_err(h, NLB_ERR_UNKNOWN_FCN, "unknown residual id");
+    const FcnInfo& fi = fcn_table()[fcn_id];
+    if (fi.m != 0) { if (*m != 0 && *m != fi.m) return set_err(h, NLB_ERR_SIZE, "m does not match the residual"); *m = fi.m; }
+    if (fi.n != 0) { if (*n != 0 && *n != fi.n) return set_err(h, NLB_ERR_SIZE, "n does not match the residual"); *n = fi.n; }
+    if (fcn_id == FCN_EXT_ROSENBROCK) {
+        if (*m == 0) *m = *n;
+        if (*m != *n || (*n & 1)) return set_err(h, NLB_ERR_SIZE, "ext_rosenbrock needs m == n, n even");
+    }
+    if (*m <= 0 || *n <= 0) return set_err(h, NLB_ERR_SIZE, "m and n must be positive");
+    *sys_len = fi.sys_len < 0 ? *m : fi.sys_len;
+    *shared_len = fi.shared_len < 0 ? *m : fi.shared_len;
+    return NLB_OK;
+}
+
+int ensure_device(nlb_handle* h) {
+    if (!h) return NLB_ERR_INVALID_ARGUMENT;
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) return set_err(h, NLB_ERR_NO_DEVICE, "cudaSetDevice", e);
+    return NLB_OK;
+}
+
+int solve_batch(nlb_handle* h, int solver, const nlb_params* params, int fcn_id, int64_t B, int m, int n, double* x,
+                double* fvec, const double* sys, const double* shared, nlb_iteration_behavior* ib, int32_t* status,
+                void* stream) {
+    if (!h) return NLB_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(h->mu);
+    if (!params || B < 0 || (B > 0 && (!x || !fvec))) return set_err(h, NLB_ERR_INVALID_ARGUMENT, "null argument or B < 0");
+    int sys_len, shared_len;
+    int rc = check_sizes(h, fcn_id, &m, &n, &sys_len, &shared_len);
+    if (rc) return rc;
+    if (solver == SOLVER_LM && n > m) return set_err(h, NLB_ERR_SIZE, "least squares needs m >= n");
+    if (solver != SOLVER_LM && n != m) return set_err(h, NLB_ERR_SIZE, "Newton / quasi-Newton need m == n");
+    if (sys_len > 0 && B > 0 && !sys) return set_err(h, NLB_ERR_INVALID_ARGUMENT, "this residual needs per-system data");
+    if (shared_len > 0 && B > 0 && !shared) return set_err(h, NLB_ERR_INVALID_ARGUMENT, "this residual needs shared data");
+    rc = ensure_device(h);
+    if (rc) return rc;
+    if (B == 0) return NLB_OK;
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+
+    Staged ax, af, as, ash, aib, ast;
+    if ((rc = stage_in(h, 0, x, sizeof(double) * (size_t)n * B, true, s, &ax))) return rc;
+    if ((rc = stage_in(h, 1, fvec, sizeof(double) * (size_t)m * B, false, s, &af))) return rc;
+    if ((rc = stage_in(h, 2, sys, sizeof(double) * (size_t)sys_len * B, true, s, &as))) return rc;
+    if ((rc = stage_in(h, 3, shared, sizeof(double) * (size_t)shared_len, true, s, &ash))) return rc;
+    if ((rc = stage_in(h, 4, ib, sizeof(nlb_iteration_behavior) * (size_t)B, false, s, &aib))) return rc;
+    if ((rc = stage_in(h, 5, status, sizeof(int32_t) * (size_t)B, false, s, &ast))) return rc;
+
+    const DevParams p = to_dev(params);
+    const FcnInfo& fi = fcn_table()[fcn_id];
+    if (fi.m != 0 && fi.n != 0) {
+        switch (solver) {
+            case SOLVER_LM:
+                rc = dispatch_tps<SOLVER_LM>(h, fcn_id, p, B, (double*)ax.dev, (double*)af.dev, (const double*)as.dev,
+                                             (const double*)ash.dev, (nlb_iteration_behavior*)aib.dev, (int32_t*)ast.dev, s);
+                break;
+            case SOLVER_NEWTON:
+                rc = dispatch_tps<SOLVER_NEWTON>(h, fcn_id, p, B, (double*)ax.dev, (double*)af.dev, (const double*)as.dev,
+                                                 (const double*)ash.dev, (nlb_iteration_behavior*)aib.dev, (int32_t*)ast.dev, s);
+                break;
+            default:
+                rc = dispatch_tps<SOLVER_BROYDEN>(h, fcn_id, p, B, (double*)ax.dev, (double*)af.dev, (const double*)as.dev,
+                                                  (const double*)ash.dev, (nlb_iteration_behavior*)aib.dev, (int32_t*)ast.dev, s);
+        }
+    } else {
+        rc = launch_coop_solve(solver, fcn_id, p, B, m, n, (double*)ax.dev, (double*)af.dev, (const double*)as.dev,
+                               (const double*)ash.dev, (nlb_iteration_behavior*)aib.dev, (int32_t*)ast.dev, s,
+                               &h->launches);
+        if (rc == NLB_ERR_UNSUPPORTED) return set_err(h, rc, "no cooperative kernel for this (solver, residual, size)");
+        if (rc == NLB_ERR_CUDA) return set_err(h, rc, "cooperative kernel launch", cudaGetLastError());
+    }
+    if (rc) return rc;
+
+    const bool any_staged = ax.staged || af.staged || aib.staged || ast.staged || as.staged || ash.staged;
+    if ((rc = stage_out(h, ax, s))) return rc;
+    if ((rc = stage_out(h, af, s))) return rc;
+    if ((rc = stage_out(h, aib, s))) return rc;
+    if ((rc = stage_out(h, ast, s))) return rc;
+    if (any_staged) NLB_CUDA(h, cudaStreamSynchronize(s));
+    return NLB_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// extern "C"
+// ---------------------------------------------------------------------------------------
+extern "C" {
+
+int nlb_create(nlb_handle** handle, int device) {
+    if (!handle) return NLB_ERR_INVALID_ARGUMENT;
+    *handle = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return NLB_ERR_NO_DEVICE;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return NLB_ERR_NO_DEVICE;
+    nlb_handle* h = new nlb_handle();
+    h->device = device;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&h->dstats, sizeof(int64_t) * NLB_STAT_COUNT) != cudaSuccess) {
+        delete h;
+        return NLB_ERR_CUDA;
+    }
+    *handle = h;
+    return NLB_OK;
+}
+
+int nlb_destroy(nlb_handle* h) {
+    if (!h) return NLB_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(h->device);
+    for (int i = 0; i < nlb_handle::NSLOT; ++i)
+        if (h->dbuf[i]) cudaFree(h->dbuf[i]);
+    if (h->dstats) cudaFree(h->dstats);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return NLB_OK;
+}
+
+const char* nlb_last_error(const nlb_handle* h) { return h ? h->last_error.c_str() : "null handle"; }
+int64_t nlb_kernel_launch_count(const nlb_handle* h) { return h ? h->launches : 0; }
+
+void nlb_params_default(nlb_params* p) {
+    if (!p) return;
+    p->max_fcn_evals = 100;
+    p->fcn_tol = 1.0e-8;
+    p->var_tol = 1.0e-12;
+    p->grad_tol = 1.0e-12;
+    p->lm_factor = 100.0;
+    p->jacobian_interval = 5;
+    p->use_line_search = 1;
+    p->ls_max_fcn_evals = 100;
+    p->ls_alpha = 1.0e-4;
+    p->ls_factor = 0.1;
+    p->use_analytic_jacobian = 0;
+    p->max_iter_guard = 100000;
+}
+
+int nlb_vecfcn_count(void) { return FCN_COUNT; }
+
+int nlb_vecfcn_lookup(const char* name) {
+    if (!name) return -1;
+    for (int i = 0; i < FCN_COUNT; ++i)
+        if (std::strcmp(fcn_table()[i].name, name) == 0) return i;
+    return -1;
+}
+
+const char* nlb_vecfcn_name(int fcn_id) {
+    if (fcn_id < 0 || fcn_id >= FCN_COUNT) return nullptr;
+    return fcn_table()[fcn_id].name;
+}
+
+int nlb_vecfcn_info(int fcn_id, int* m, int* n, int* sys_len, int* shared_len, int* has_jacobian) {
+    if (fcn_id < 0 || fcn_id >= FCN_COUNT) return NLB_ERR_UNKNOWN_FCN;
+    const FcnInfo& fi = fcn_table()[fcn_id];
+    if (m) *m = fi.m;
+    if (n) *n = fi.n;
+    if (sys_len) *sys_len = fi.sys_len;
+    if (shared_len) *shared_len = fi.shared_len;
+    if (has_jacobian) *has_jacobian = fi.has_jac;
+    return NLB_OK;
+}
+
+int nlb_least_squares_solve_batch(nlb_handle* h, const nlb_params* params, int fcn_id, int64_t B, int m, int n,
+                                  double* x, double* fvec, const double* sys, const double* shared,
+                                  nlb_iteration_behavior* ib, int32_t* status, void* stream) {
+    return solve_batch(h, SOLVER_LM, params, fcn_id, B, m, n, x, fvec, sys, shared, ib, status, stream);
+}
+
+int nlb_newton_solve_batch(nlb_handle* h, const nlb_params* params, int fcn_id, int64_t B, int m, int n, double* x,
+                           double* fvec, const double* sys, const double* shared, nlb_iteration_behavior* ib,
+                           int32_t* status, void* stream) {
+    return solve_batch(h, SOLVER_NEWTON, params, fcn_id, B, m, n, x, fvec, sys, shared, ib, status, stream);
+}
+
+int nlb_quasi_newton_solve_batch(nlb_handle* h, const nlb_params* params, int fcn_id, int64_t B, int m, int n,
+                                 double* x, double* fvec, const double* sys, const double* shared,
+                                 nlb_iteration_behavior* ib, int32_t* status, void* stream) {
+    return solve_batch(h, SOLVER_BROYDEN, params, fcn_id, B, m, n, x, fvec, sys, shared, ib, status, stream);
+}
+
+int nlb_vecfcn_eval_batch(nlb_handle* h, int fcn_id, int64_t B, int m, int n, const double* x, double* fvec,
+                          const double* sys, const double* shared, void* stream) {
+    if (!h) return NLB_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(h->mu);
+    if (B < 0 || (B > 0 && (!x || !fvec))) return set_err(h, NLB_ERR_INVALID_ARGUMENT, "null argument or B < 0");
+    int sys_len, shared_len;
+    int rc = check_sizes(h, fcn_id, &m, &n, &sys_len, &shared_len);
+    if (rc) return rc;
+    if ((rc = ensure_device(h))) return rc;
+    if (B == 0) return NLB_OK;
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    Staged ax, af, as, ash;
+    if ((rc = stage_in(h, 0, x, sizeof(double) * (size_t)n * B, true, s, &ax))) return rc;
+    if ((rc = stage_in(h, 1, fvec, sizeof(double) * (size_t)m * B, false, s, &af))) return rc;
+    if ((rc = stage_in(h, 2, sys, sizeof(double) * (size_t)sys_len * B, true, s, &as))) return rc;
+    if ((rc = stage_in(h, 3, shared, sizeof(double) * (size_t)shared_len, true, s, &ash))) return rc;
+    const unsigned grid = (unsigned)((B + TPS_BLOCK - 1) / TPS_BLOCK);
+    switch (fcn_id) {
+#define X(F)                                                                                                   \
+    case F::ID:                                                                                                \
+        tps_eval_kernel<F><<<grid, TPS_BLOCK, 0, s>>>(B, (const double*)ax.dev, (double*)af.dev,               \
+                                                      (const double*)as.dev, (const double*)ash.dev);          \
+        break;
+        NLB_FIXED_FCNS(X)
+#undef X
+        default:
+            rc = launch_coop_eval(fcn_id, B, m, n, (const double*)ax.dev, (double*)af.dev, (const double*)as.dev,
+                                  (const double*)ash.dev, s);
+            if (rc) return set_err(h, rc, "no evaluation kernel for this residual");
+    }
+    ++h->launches;
+    NLB_CUDA(h, cudaGetLastError());
+    if ((rc = stage_out(h, af, s))) return rc;
+    if (ax.staged || af.staged || as.staged || ash.staged) NLB_CUDA(h, cudaStreamSynchronize(s));
+    return NLB_OK;
+}
+
+int nlb_jacobian_batch(nlb_handle* h, const nlb_params* params, int fcn_id, int64_t B, int m, int n, const double* x,
+                       double* jac, const double* sys, const double* shared, void* stream) {
+    if (!h) return NLB_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(h->mu);
+    if (!params || B < 0 || (B > 0 && (!x || !jac))) return set_err(h, NLB_ERR_INVALID_ARGUMENT, "null argument or B < 0");
+    int sys_len, shared_len;
+    int rc = check_sizes(h, fcn_id, &m, &n, &sys_len, &shared_len);
+    if (rc) return rc;
+    if ((rc = ensure_device(h))) return rc;
+    if (B == 0) return NLB_OK;
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    Staged ax, aj, as, ash;
+    if ((rc = stage_in(h, 0, x, sizeof(double) * (size_t)n * B, true, s, &ax))) return rc;
+    if ((rc = stage_in(h, 1, jac, sizeof(double) * (size_t)m * n * B, false, s, &aj))) return rc;
+    if ((rc = stage_in(h, 2, sys, sizeof(double) * (size_t)sys_len * B, true, s, &as))) return rc;
+    if ((rc = stage_in(h, 3, shared, sizeof(double) * (size_t)shared_len, true, s, &ash))) return rc;
+    const unsigned grid = (unsigned)((B + TPS_BLOCK - 1) / TPS_BLOCK);
+    switch (fcn_id) {
+#define X(F)                                                                                                    \
+    case F::ID:                                                                                                 \
+        tps_jacobian_kernel<F><<<grid, TPS_BLOCK, 0, s>>>(params->use_analytic_jacobian, B, (const double*)ax.dev, \
+                                                          (double*)aj.dev, (const double*)as.dev,               \
+                                                          (const double*)ash.dev);                              \
+        break;
+        NLB_FIXED_FCNS(X)
+#undef X
+        default: return set_err(h, NLB_ERR_UNSUPPORTED, "no Jacobian kernel for this residual");
+    }
+    ++h->launches;
+    NLB_CUDA(h, cudaGetLastError());
+    if ((rc = stage_out(h, aj, s))) return rc;
+    if (ax.staged || aj.staged || as.staged || ash.staged) NLB_CUDA(h, cudaStreamSynchronize(s));
+    return NLB_OK;
+}
+
+int nlb_reduce_stats(nlb_handle* h, int64_t B, const nlb_iteration_behavior* ib, const int32_t* status,
+                     int64_t* stats, void* stream) {
+    if (!h) return NLB_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(h->mu);
+    if (!stats || B < 0) return set_err(h, NLB_ERR_INVALID_ARGUMENT, "null stats or B < 0");
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    Staged aib, ast;
+    if ((rc = stage_in(h, 4, ib, sizeof(nlb_iteration_behavior) * (size_t)B, true, s, &aib))) return rc;
+    if ((rc = stage_in(h, 5, status, sizeof(int32_t) * (size_t)B, true, s, &ast))) return rc;
+    const bool out_dev = is_device_ptr(stats);
+    int64_t* d = out_dev ? stats : h->dstats;
+    NLB_CUDA(h, cudaMemsetAsync(d, 0, sizeof(int64_t) * NLB_STAT_COUNT, s));
+    if (B > 0) {
+        unsigned grid = (unsigned)((B + 255) / 256);
+        if (grid > 148u * 8u) grid = 148u * 8u;
+        stats_kernel<<<grid, 256, 0, s>>>(B, (const nlb_iteration_behavior*)aib.dev, (const int32_t*)ast.dev,
+                                          (unsigned long long*)d);
+        ++h->launches;
+        NLB_CUDA(h, cudaGetLastError());
+    }
+    if (!out_dev) {
+        NLB_CUDA(h, cudaMemcpyAsync(stats, d, sizeof(int64_t) * NLB_STAT_COUNT, cudaMemcpyDeviceToHost, s));
+        NLB_CUDA(h, cudaStreamSynchronize(s));
+    }
+    return NLB_OK;
+}
+
+int nlb_measure_fp64_peak(nlb_handle* h, double* dfma_tflops, double* dadd_dmul_tflops) {
+    if (!h) return NLB_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(h->mu);
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    cudaDeviceProp prop;
+    NLB_CUDA(h, cudaGetDeviceProperties(&prop, h->device));
+    const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 20000;
+    double* dout = (double*)h->dstats;
+    cudaEvent_t e0, e1;
+    NLB_CUDA(h, cudaEventCreate(&e0));
+    NLB_CUDA(h, cudaEventCreate(&e1));
+    double res[2] = {0.0, 0.0};
+    for (int variant = 0; variant < 2; ++variant) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            NLB_CUDA(h, cudaEventRecord(e0, h->stream));
+            if (variant == 0) fp64_peak_kernel<true><<<blocks, threads, 0, h->stream>>>(dout, iters, 1.0);
+            else fp64_peak_kernel<false><<<blocks, threads, 0, h->stream>>>(dout, iters, 1.0);
+            ++h->launches;
+            NLB_CUDA(h, cudaEventRecord(e1, h->stream));
+            NLB_CUDA(h, cudaEventSynchronize(e1));
+            float ms = 0.f;
+            NLB_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        const double flops = 2.0 * 8.0 * (double)iters * (double)threads * (double)blocks;
+        res[variant] = flops / (best * 1e-3) / 1e12;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (dfma_tflops) *dfma_tflops = res[0];
+    if (dadd_dmul_tflops) *dadd_dmul_tflops = res[1];
+    return NLB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,460 @@
+#!/usr/bin/env python
+"""bench.py — converged systems / second of the batched nonlinear-solve hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2] [--impl engine|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one synthetic batch: one solve kernel over
+B = 2^20 systems per GPU (inputs already resident in HBM) followed by the statistics kernel
+that counts the converged systems.  The default workload is BASELINE.json configs[1]:
+1M x README Example 1 (2x2, quasi_newton_solver, perturbed x0).  With N GPUs every rank solves
+its own 2^20-system shard (weak scaling, no data-path collective); the per-rank statistics are
+combined with one 128-byte all-gather per step.
+
+One JSON line is printed by rank 0 (schema: the bench contract in the task description).
+  value      converged systems / s, all ranks, device-resident inputs, CUDA-event time (max over ranks)
+  e2e        same metric through the public solver object with pinned HOST buffers: H2D of x0 (and
+             per-system data) and D2H of x, fvec, iteration_behavior, status inside the timed region
+  roofline   dominant kernel (the solve kernel) against the FP64 pipe: algorithmic FP64 operations
+             per system (counted by the oracle's counting build on a sample of the same batch) x
+             systems / CUDA-event time of that kernel, against the DFMA peak measured on this GPU;
+             plus the HBM side (algorithmic bytes per system from SURVEY.md §8d) for reference
+  cpu_baseline  the CPU oracle (a port; the Fortran reference cannot be built in this image) on all
+             host cores, same batch
+`--impl reference` times that CPU port alone and prints the same line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "converged systems/sec"
+UNIT = "systems/s"
+BATCH_PER_GPU = 1 << 20
+L2_FLUSH_BYTES = 256 << 20
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--batch", type=int, default=0, help="systems per GPU (default: 2^20; smaller for C4/C5)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short runs of the other workloads")
+    return ap.parse_args()
+
+
+def default_batch(name):
+    return {"C4": 4096, "C5": 16384}.get(name, BATCH_PER_GPU)
+
+
+def workload_label(w, B):
+    desc = {
+        "C1": "1M x README Example 2 cubic fit (m=21, n=4), least_squares_solver, per-system noisy y",
+        "C2": "1M x README Example 1 (2x2), quasi_newton_solver, perturbed x0",
+        "C3": "1M x Powell badly scaled (2x2), newton_solver + line search, max_fcn_evals=1000",
+        "C4": "LM curve fits m=4096 x n=16 (rational 7/8 model)",
+        "C5": "extended Rosenbrock n=64, quasi_newton_solver + line search",
+        "LM4": "4-parameter double-exponential LM fits, m=64",
+    }[w["name"]]
+    return "%s [BASELINE config %s], B=%d per GPU" % (desc, w["name"], B)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler (NVML in a thread; nvidia-smi would be too slow for a sub-second timed region)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {
+        0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+        0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+        0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU oracle legs
+# ---------------------------------------------------------------------------------------------
+def oracle_params(o, w):
+    kw = {}
+    if "set_max_fcn_evals" in w["settings"]:
+        kw["max_fcn_evals"] = w["settings"]["set_max_fcn_evals"]
+    return o.params(**kw)
+
+
+def cpu_port_throughput(w, min_seconds=4.0, max_reps=50, sample=None):
+    """Time the CPU oracle (OpenMP, all host cores) on the workload's batch (or a slice of it)."""
+    from oracle.nl_oracle import Oracle
+
+    o = Oracle()
+    B = w["x0"].shape[1]
+    nsub = min(B, sample or B)
+    x0 = np.ascontiguousarray(w["x0"][:, :nsub])
+    sysd = None if w["args"] is None else np.ascontiguousarray(w["args"][:, :nsub])
+    p = oracle_params(o, w)
+    cores = os.cpu_count() or 1
+    o.solve_batch(w["solver"], w["fcn"], x0[:, : min(nsub, 4096)].copy(), m=w["m"],
+                  sys=None if sysd is None else sysd[:, : min(nsub, 4096)].copy(), shared=w["shared"], params=p)
+    reps, elapsed, conv = 0, 0.0, 0
+    while (elapsed < min_seconds and reps < max_reps) or reps < 2:
+        t0 = time.perf_counter()
+        _, _, _, st = o.solve_batch(w["solver"], w["fcn"], x0, m=w["m"], sys=sysd, shared=w["shared"], params=p, nthreads=cores)
+        elapsed += time.perf_counter() - t0
+        conv += int((st == 0).sum())
+        reps += 1
+    return {"value": conv / elapsed, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d systems of the batch x %d passes, OpenMP schedule(dynamic), one system per thread at a time" % (nsub, reps)}
+
+
+def flops_per_system(w, sample=4096):
+    """Algorithmic FP64 operations (+ - * / sqrt, exp = 25) per system: counting build of the oracle."""
+    from oracle.nl_oracle import Oracle
+
+    o = Oracle(counting=True)
+    B = w["x0"].shape[1]
+    idx = np.linspace(0, B - 1, min(sample, B)).astype(np.int64)
+    x0 = np.ascontiguousarray(w["x0"][:, idx])
+    sysd = None if w["args"] is None else np.ascontiguousarray(w["args"][:, idx])
+    o.flops_reset()
+    o.solve_batch(w["solver"], w["fcn"], x0, m=w["m"], sys=sysd, shared=w["shared"], params=oracle_params(o, w))
+    return o.flops_total() / float(idx.size)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path.  The Fortran sources need gfortran + the external
+    linalg package, neither of which exists in this image, so this arm times the C++ port (oracle/)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from nonlin_b200 import workloads as W
+
+    B = args.batch or default_batch(args.workload)
+    w = W.WORKLOADS[args.workload](B)
+    from oracle.nl_oracle import Oracle
+
+    o = Oracle()
+    p = oracle_params(o, w)
+    cores = os.cpu_count() or 1
+    # bounded sample per step so that K steps finish within minutes
+    nsub = B if args.workload in ("C1", "C2", "C3", "LM4") else min(B, 256)
+    x0 = np.ascontiguousarray(w["x0"][:, :nsub]); sysd = None if w["args"] is None else np.ascontiguousarray(w["args"][:, :nsub])
+    for _ in range(args.warmup):
+        o.solve_batch(w["solver"], w["fcn"], x0, m=w["m"], sys=sysd, shared=w["shared"], params=p, nthreads=cores)
+    t0 = time.perf_counter(); conv = 0
+    for _ in range(args.steps):
+        _, _, _, st = o.solve_batch(w["solver"], w["fcn"], x0, m=w["m"], sys=sysd, shared=w["shared"], params=p, nthreads=cores)
+        conv += int((st == 0).sum())
+    dt = time.perf_counter() - t0
+    val = conv / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_label(w, B), "sample_per_step": nsub},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d systems per step, OpenMP over all host cores; C++ port of the Fortran path "
+                                   "(no Fortran compiler / linalg in the image)" % nsub},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# engine arm
+# ---------------------------------------------------------------------------------------------
+def make_solver(nb, w):
+    s = {"least_squares": nb.least_squares_solver, "newton": nb.newton_solver, "quasi_newton": nb.quasi_newton_solver}[w["solver"]]()
+    for k, v in w["settings"].items():
+        getattr(s, k)(v)
+    return s
+
+
+class DeviceRun:
+    """One workload resident on one GPU, ready to be stepped."""
+
+    def __init__(self, nb, torch, w, eng, nbuf):
+        self.nb, self.torch, self.w, self.eng = nb, torch, w, eng
+        self.B = w["x0"].shape[1]
+        dev = torch.device("cuda", eng.device)
+        self.obj = nb.vecfcn_helper(); self.obj.set_fcn(w["fcn"], w["m"], w["n"])
+        if w["shared"] is not None:
+            self.obj.set_shared_data(torch.from_numpy(w["shared"]).to(dev))
+        self.solver = make_solver(nb, w)
+        self.x0 = torch.from_numpy(w["x0"]).to(dev)
+        self.args = None if w["args"] is None else torch.from_numpy(w["args"]).to(dev)
+        # the solve is in place: one fresh copy of x0 per step, made before the timed region
+        self.xs = [self.x0.clone() for _ in range(nbuf)]
+        self.f = torch.empty((w["m"], self.B), dtype=torch.float64, device=dev)
+        self.ib = nb.iteration_behavior(self.B, like=self.x0)
+        self.status = torch.zeros(self.B, dtype=torch.int32, device=dev)
+        self.stats = torch.zeros(16, dtype=torch.int64, device=dev)
+        self.flush = torch.empty(L2_FLUSH_BYTES // 8, dtype=torch.float64, device=dev)
+
+    def step(self, k, dist_on):
+        self.solver.solve(self.obj, self.xs[k], self.f, self.ib, args=self.args, status=self.status)
+        self.eng.reduce_stats_device(self.ib, self.status, self.stats, self.B)
+        if dist_on:
+            from nonlin_b200.distributed import allreduce_stats
+
+            allreduce_stats(self.stats)
+
+    def timed(self, steps, warmup, dist_on, sampler=None):
+        torch = self.torch
+        for k in range(warmup):
+            self.flush.fill_(0.0)
+            self.step(k, dist_on)
+        torch.cuda.synchronize()
+        e0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        e1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        es = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        if dist_on:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
+        l0 = self.eng.kernel_launches
+        for k in range(steps):
+            self.flush.fill_(0.0)                      # L2 flush between timed steps (not timed)
+            e0[k].record()
+            self.solver.solve(self.obj, self.xs[warmup + k], self.f, self.ib, args=self.args, status=self.status)
+            es[k].record()                             # end of the dominant (solve) kernel
+            self.eng.reduce_stats_device(self.ib, self.status, self.stats, self.B)
+            if dist_on:
+                from nonlin_b200.distributed import allreduce_stats
+
+                allreduce_stats(self.stats)
+            e1[k].record()
+        torch.cuda.synchronize()
+        launches = self.eng.kernel_launches - l0
+        clocks = sampler.stop() if sampler else None
+        if dist_on:
+            import torch.distributed as dist
+
+            dist.barrier()
+        step_ms = sum(a.elapsed_time(b) for a, b in zip(e0, e1))
+        solve_ms = sum(a.elapsed_time(b) for a, b in zip(e0, es))
+        return step_ms, solve_ms, launches, clocks
+
+
+def e2e_run(nb, torch, w, eng, steps, warmup):
+    """Public API with pinned HOST buffers: H2D + kernel + D2H per step, timed with CUDA events on
+    the stream the engine is told to use."""
+    B = w["x0"].shape[1]
+    obj = nb.vecfcn_helper(); obj.set_fcn(w["fcn"], w["m"], w["n"])
+    if w["shared"] is not None:
+        obj.set_shared_data(w["shared"])
+    solver = make_solver(nb, w)
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    x0 = pin(w["x0"]); args = None if w["args"] is None else pin(w["args"])
+    x = torch.empty_like(x0).pin_memory()
+    f = torch.empty((w["m"], B), dtype=torch.float64).pin_memory()
+    ib = torch.zeros((B, 7), dtype=torch.int32).pin_memory()
+    st = torch.zeros(B, dtype=torch.int32).pin_memory()
+    stream = torch.cuda.current_stream().cuda_stream or 1
+    h2d = x0.numel() * 8 + (0 if args is None else args.numel() * 8) + (0 if w["shared"] is None else w["shared"].size * 8)
+    d2h = x.numel() * 8 + f.numel() * 8 + ib.numel() * 4 + st.numel() * 4
+    total_ms, conv = 0.0, 0
+    for k in range(warmup + steps):
+        x.copy_(x0)
+        torch.cuda.synchronize()
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        solver.solve(obj, x, f, ib, args=args, status=st, stream=stream)
+        b.record(); torch.cuda.synchronize()
+        if k >= warmup:
+            total_ms += a.elapsed_time(b)
+            conv += int((st == 0).sum())      # device->host result read: the status array
+    return total_ms, conv, h2d, d2h
+
+
+def run_engine(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device. The engine has no CPU fallback (use --impl reference for the CPU port).")
+    torch.cuda.set_device(local)
+    dist_on = world > 1
+    if dist_on:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import nonlin_b200 as nb
+    from nonlin_b200 import workloads as W
+
+    eng = nb.default_engine(local)
+    B = args.batch or default_batch(args.workload)
+    w = W.WORKLOADS[args.workload](B, seed=1000 + rank)          # every rank its own shard (weak scaling)
+    peak = eng.measure_fp64_peak()                               # also spins the clocks up
+    run = DeviceRun(nb, torch, w, eng, args.steps + args.warmup)
+    sampler = ClockSampler(local) if rank == 0 else None
+    step_ms, solve_ms, launches, clocks = run.timed(args.steps, args.warmup, dist_on, sampler)
+    conv_local = int(run.stats[1].item()) if not dist_on else None
+    stats = run.stats.clone()
+    t = torch.tensor([step_ms, solve_ms], dtype=torch.float64, device="cuda")
+    if dist_on:
+        import torch.distributed as dist
+
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)                 # device time = max over ranks
+    step_ms, solve_ms = float(t[0]), float(t[1])
+    from nonlin_b200.distributed import stats_dict
+
+    sd = stats_dict(stats)                                       # already summed over ranks when dist_on
+    total_systems = sd["systems"]
+    converged = sd["converged"]
+    value = converged * args.steps / (step_ms * 1e-3)
+
+    # e2e through the public API with host buffers (each rank its shard, max over ranks)
+    e2e_steps = max(3, min(args.steps, 10))
+    e_ms, e_conv, h2d, d2h = e2e_run(nb, torch, w, eng, e2e_steps, 3)
+    te = torch.tensor([e_ms], dtype=torch.float64, device="cuda"); tc = torch.tensor([e_conv], dtype=torch.int64, device="cuda")
+    if dist_on:
+        import torch.distributed as dist
+
+        dist.all_reduce(te, op=dist.ReduceOp.MAX); dist.all_reduce(tc, op=dist.ReduceOp.SUM)
+    e2e_value = float(tc[0]) / (float(te[0]) * 1e-3)
+
+    if rank != 0:
+        if dist_on:
+            import torch.distributed as dist
+
+            dist.barrier(); dist.destroy_process_group()
+        return
+
+    # roofline of the dominant kernel (solve kernel), rank 0's launch
+    fl = flops_per_system(w)
+    kernel_s = solve_ms * 1e-3 / args.steps
+    achieved_tf = fl * B / kernel_s / 1e12
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak, hbm_src = 6650.0, "fallback"
+    if os.path.exists(peaks_file):
+        try:
+            hbm_peak, hbm_src = float(json.load(open(peaks_file))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    hbm_ach = w["bytes_per_system"] * B / kernel_s / 1e9
+    traffic = None
+    tf = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tf):
+        try:
+            traffic = json.load(open(tf)).get(args.workload)
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "fp64", "kernel": "tps_solve_kernel" if w["name"] in ("C1", "C2", "C3") else "coop_solve_kernel",
+        "achieved": achieved_tf, "peak": peak["dfma_tflops"], "unit": "TFLOP/s", "frac": achieved_tf / peak["dfma_tflops"],
+        "peak_source": "DFMA micro-kernel measured on this GPU at run time (MEASURED_PEAKS.json has no FP64 entry)",
+        "peak_no_fma": peak["dadd_dmul_tflops"], "frac_of_no_fma_peak": achieved_tf / peak["dadd_dmul_tflops"],
+        "flops_per_system": fl, "kernel_ms": kernel_s * 1e3,
+        "note": "parity build issues DMUL+DADD instead of DFMA (-fmad=false), so its own ceiling is peak_no_fma",
+        "traffic": traffic,
+        "hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                "bytes_per_system": w["bytes_per_system"], "peak_source": hbm_src},
+    }
+    cpu = cpu_port_throughput(w) if world == 1 else None
+
+    extras = {}
+    if not args.no_extras and world == 1:
+        for name in ("C1", "C3"):
+            if name == args.workload:
+                continue
+            try:
+                we = W.WORKLOADS[name](default_batch(name), seed=1000)
+                r = DeviceRun(nb, torch, we, eng, 5 + 3)
+                sm, km, _, _ = r.timed(5, 3, False)
+                c = int(r.stats[1].item())
+                fle = flops_per_system(we, 1024)
+                extras[name] = {"workload": workload_label(we, default_batch(name)), "value": c * 5 / (sm * 1e-3), "unit": UNIT,
+                                "ms_per_step": sm / 5, "fp64_tflops": fle * default_batch(name) / (km / 5 * 1e-3) / 1e12,
+                                "flops_per_system": fle}
+                del r
+            except Exception as ex:   # an extra must never hide the headline
+                extras[name] = {"error": repr(ex)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_label(w, B), "systems_per_step_all_gpus": total_systems,
+                   "converged_per_step": converged, "parallelism": "dp%d (contiguous system shards, no data-path collective)" % world,
+                   "l2": "flushed between timed steps (256 MiB write, untimed); per-step CUDA events summed",
+                   "arithmetic": "FP64, no FMA contraction (bit-identical to the CPU oracle)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "how": "solver.solve() on pinned host buffers; CUDA events around H2D + kernel + D2H"},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "stats": sd,
+        "other_workloads": extras,
+    }
+    print(json.dumps(line))
+    if dist_on:
+        import torch.distributed as dist
+
+        dist.barrier(); dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -355,8 +355,11 @@ class equation_solver:
         p.use_analytic_jacobian = int(fcn.is_jacobian_defined())
         return p
 
-    def solve(self, fcn, x, fvec=None, ib=None, args=None, status=None):
+    def solve(self, fcn, x, fvec=None, ib=None, args=None, status=None, stream=None):
         """Solve the B systems in x (n, B) in place. Returns the per-system status array.
+
+        `stream` (a raw cudaStream_t integer) overrides the stream choice: by default CUDA tensors
+        run on torch's current stream and host arrays on the engine's own stream.
 
         Mirrors `call solver%solve(fcn, x, fvec, ib, args)` (nonlin_solver interface,
         src/nonlin_multi_eqn_mult_var.f90:94-119).
@@ -384,7 +387,8 @@ class equation_solver:
         p = self._params(fcn)
         entry = getattr(_LIB, self._entry)
         eng.check(entry(eng._h, C.byref(p), fcn._fcn_id, B, m, n, _ptr(x), _ptr(fvec), _ptr(args), _ptr(fcn._shared),
-                        _ptr(ib), _ptr(status), _stream_of(x, fvec, args, ib, status)))
+                        _ptr(ib), _ptr(status),
+                        C.c_void_p(stream) if stream is not None else _stream_of(x, fvec, args, ib, status)))
         self.last_fvec = fvec
         return status
 

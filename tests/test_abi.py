@@ -1,0 +1,103 @@
+"""The C-ABI library loads and exports every symbol include/nonlin_batch.h declares; struct
+layouts, defaults and the residual registry agree with the header and with the oracle's
+independent table.  No compute calls (CPU only)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = open(os.path.join(ROOT, "include", "nonlin_batch.h")).read()
+
+
+def declared_functions():
+    names = re.findall(r"^(?:int|void|const char\*|int64_t)\s+(nlb_\w+)\s*\(", HEADER, flags=re.M)
+    assert len(names) >= 16
+    return names
+
+
+def test_library_exports_every_declared_symbol():
+    from nonlin_b200 import _lib
+
+    lib = C.CDLL(_lib.LIB_PATH)
+    for name in declared_functions():
+        assert hasattr(lib, name), "libnonlin_b200.so does not export %s" % name
+    assert sorted(declared_functions()) == sorted(_lib.EXPORTS)
+
+
+def test_every_entry_point_cites_the_reference():
+    # each solver / helper entry point names the reference procedure and file:line it replaces
+    for proc in ("lss_solve, src/nonlin_least_squares.f90:118-391", "ns_solve, src/nonlin_solve.f90:452-638",
+                 "qns_solve, src/nonlin_solve.f90:156-425", "vfh_jac_fcn, src/nonlin_multi_eqn_mult_var.f90:198-277",
+                 "vfh_fcn, src/nonlin_multi_eqn_mult_var.f90:178-195", "src/nonlin_types.f90:8-29"):
+        assert proc in HEADER
+
+
+def test_struct_layouts_and_defaults():
+    from nonlin_b200 import _lib
+
+    lib = _lib.load()
+    assert _lib.IB_DTYPE.itemsize == 28                      # 4 x int32 + 3 x default LOGICAL
+    p = _lib.nlb_params()
+    lib.nlb_params_default(C.byref(p))
+    # defaults of the reference's solver objects (SURVEY.md §5 "Config / flags")
+    assert (p.max_fcn_evals, p.fcn_tol, p.var_tol, p.grad_tol) == (100, 1e-8, 1e-12, 1e-12)
+    assert (p.lm_factor, p.jacobian_interval, p.use_line_search) == (100.0, 5, 1)
+    assert (p.ls_max_fcn_evals, p.ls_alpha, p.ls_factor, p.use_analytic_jacobian) == (100, 1e-4, 0.1, 0)
+    # status codes in the header and in the Python mirror agree
+    for name, val in re.findall(r"#define NLB_(\w+_ERROR) (\d+)", HEADER):
+        assert getattr(_lib, "NL_" + name) == int(val)
+
+
+def test_params_struct_matches_oracle_struct(oracle):
+    from nonlin_b200 import _lib
+    from oracle.nl_oracle import Params
+
+    assert [f[0] for f in Params._fields_] == [f[0] for f in _lib.nlb_params._fields_]
+    assert C.sizeof(Params) == C.sizeof(_lib.nlb_params)
+
+
+def test_registry_matches_oracle_table(oracle):
+    """Two independently written tables (CUDA registry, oracle problems) describe the same residuals."""
+    from nonlin_b200 import _lib
+
+    lib = _lib.load()
+    n = lib.nlb_vecfcn_count()
+    assert n == 12
+    for fid in range(n):
+        name = lib.nlb_vecfcn_name(fid).decode()
+        assert lib.nlb_vecfcn_lookup(name.encode()) == fid
+        assert oracle.fcn_id(name) == fid
+        vals = [C.c_int() for _ in range(5)]
+        assert lib.nlb_vecfcn_info(fid, *[C.byref(v) for v in vals]) == 0
+        info = oracle.fcn_info(fid)
+        assert [v.value for v in vals] == [info["m"], info["n"], info["sys_len"], info["shared_len"], info["has_jac"]]
+    assert lib.nlb_vecfcn_lookup(b"no_such_fcn") == -1
+    assert lib.nlb_vecfcn_name(99) is None
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import nonlin_b200 as nb
+
+    with pytest.raises(nb.NonlinError) as e:
+        nb.Engine(0)
+    assert e.value.code == nb.NLB_ERR_NO_DEVICE
+    obj = nb.vecfcn_helper(); obj.set_fcn("misc_2fcn", 2, 2)
+    with pytest.raises(nb.NonlinError):
+        nb.quasi_newton_solver().solve(obj, np.ones((2, 4)))
+
+
+def test_product_does_not_touch_the_oracle():
+    """Nothing under nonlin_b200/ or include/ may import, include or link anything under oracle/."""
+    for base in ("nonlin_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for fn in files:
+                if fn.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".f90")):
+                    src = open(os.path.join(dirpath, fn)).read()
+                    assert "nl_oracle" not in src and "oracle/" not in src and "import oracle" not in src, fn

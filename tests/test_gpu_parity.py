@@ -1,0 +1,333 @@
+"""GPU parity tests: the CUDA engine, called through its public interface (the Python mirror of
+the reference's solver objects over the C ABI), against the CPU oracle on the same seeded
+inputs, against the committed golden vectors, and through size-independent properties at
+full batch size.
+
+Bar (BASELINE.json north_star): converged x and f within 1e-10 relative, iteration /
+function-evaluation / Jacobian counts equal on >= 99 % of systems.  The thread-per-system
+kernels keep the reference's operation order and run without FMA contraction, so the tests
+below assert the stronger property: bit-identical x, f, counts and status on every system.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REL_TOL = 1e-10        # north_star tolerance on converged x and f
+COUNT_MATCH_MIN = 0.99  # north_star bar on (iter, nfev, njac) equality
+
+
+def make_solver(nb, w, **extra):
+    cls = {"least_squares": nb.least_squares_solver, "newton": nb.newton_solver, "quasi_newton": nb.quasi_newton_solver}
+    s = cls[w["solver"]]()
+    for k, v in list(w["settings"].items()) + list(extra.items()):
+        getattr(s, k)(v)
+    return s
+
+
+def oracle_params(oracle, w, **extra):
+    kw = {}
+    if "set_max_fcn_evals" in w["settings"]:
+        kw["max_fcn_evals"] = w["settings"]["set_max_fcn_evals"]
+    kw.update(extra)
+    return oracle.params(**kw)
+
+
+def run_engine(nb, w, solver=None, analytic=False, B=None):
+    B = B or w["x0"].shape[1]
+    obj = nb.vecfcn_helper()
+    obj.set_fcn(w["fcn"], w["m"], w["n"])
+    if w["shared"] is not None:
+        obj.set_shared_data(w["shared"])
+    if analytic:
+        obj.set_jacobian()
+    s = solver or make_solver(nb, w)
+    x = w["x0"].copy()
+    f = np.zeros((w["m"], B))
+    ib = nb.iteration_behavior(B)
+    st = s.solve(obj, x, f, ib, args=w["args"])
+    return x, f, ib, st
+
+
+def assert_parity(x, f, ib, st, xo, fo, ibo, sto, bitwise=True):
+    counts = ((ib["iter_count"] == ibo["iter_count"]) & (ib["fcn_count"] == ibo["fcn_count"])
+              & (ib["jacobian_count"] == ibo["jacobian_count"]))
+    assert counts.mean() >= COUNT_MATCH_MIN
+    assert np.array_equal(st, sto)
+    ok = sto == 0
+    scale_x = np.maximum(np.abs(xo), 1e-300)
+    assert np.all(np.abs(x - xo)[:, ok] <= REL_TOL * np.maximum(scale_x[:, ok], np.abs(xo[:, ok]).max(axis=0)))
+    assert np.all(np.abs(f - fo)[:, ok] <= REL_TOL * np.maximum(np.abs(fo[:, ok]).max(axis=0), 1e-300) + 1e-300)
+    if bitwise:
+        assert np.array_equal(x, xo) and np.array_equal(f, fo)
+        assert counts.all()
+        for k in ("converge_on_fcn", "converge_on_chng", "converge_on_zero_diff", "gradient_count"):
+            assert np.array_equal(ib[k], ibo[k])
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE configs on the thread-per-system kernels
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,B", [("C1", 4096), ("C2", 8192), ("C3", 8192)])
+def test_config_parity_vs_oracle(engine, oracle, name, B):
+    import nonlin_b200 as nb
+    from nonlin_b200 import workloads as W
+
+    w = W.WORKLOADS[name](B)
+    x, f, ib, st = run_engine(nb, w)
+    xo, fo, ibo, sto = oracle.solve_batch(w["solver"], w["fcn"], w["x0"], m=w["m"], sys=w["args"], shared=w["shared"],
+                                          params=oracle_params(oracle, w))
+    assert (sto == 0).mean() > 0.99
+    assert_parity(x, f, ib, st, xo, fo, ibo, sto)
+
+
+@pytest.mark.parametrize("name", ["C1", "C2", "C3"])
+def test_config_parity_vs_committed_golden(engine, name):
+    import nonlin_b200 as nb
+    from nonlin_b200 import workloads as W
+
+    g = np.load(os.path.join(HERE, "golden", "oracle_batches.npz"))
+    B = g[name + "_status"].shape[0]
+    w = W.WORKLOADS[name](B)
+    x, f, ib, st = run_engine(nb, w)
+    assert np.array_equal(x, g[name + "_x"]) and np.array_equal(f, g[name + "_f"])
+    assert np.array_equal(ib.view(np.int32).reshape(B, 7), g[name + "_ib"])
+    assert np.array_equal(st, g[name + "_status"])
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's own test table (tests/nonlin_test_solve.f90), B = many identical copies
+# ---------------------------------------------------------------------------------------------
+TABLE = [
+    # solver, fcn, x0, analytic, settings, expected |x|, tol                       reference test
+    ("quasi_newton", "misc_2fcn", (0.5, 0.5), True, {}, (5, 3), 1e-6),           # test_quasinewton_1
+    ("quasi_newton", "misc_2fcn", (1.0, 1.0), True, {}, (5, 3), 1e-6),
+    ("quasi_newton", "poorly_scaled_2fcn", (0.5, 0.5), False, {"set_use_line_search": False}, (5000, 10), 1e-6),  # _2
+    ("quasi_newton", "poorly_scaled_2fcn", (1.0, 1.0), False, {"set_use_line_search": False}, (5000, 10), 1e-6),
+    ("quasi_newton", "misc_2fcn_a", (0.5, 0.5), False, {}, (5, 3), 1e-6),        # test_quasinewton_3 (args = 2.0)
+    ("quasi_newton", "misc_2fcn_a", (1.0, 1.0), True, {}, (5, 3), 1e-6),
+    ("quasi_newton", "powell_badly_scaled", (0.0, 1.0), True, {"set_use_line_search": False}, (1.098159e-5, 9.106146), 1e-5),  # _4
+    ("newton", "misc_2fcn", (0.5, 0.5), True, {}, (5, 3), 1e-6),                 # test_newton_1
+    ("newton", "misc_2fcn", (1.0, 1.0), True, {}, (5, 3), 1e-6),
+    ("newton", "poorly_scaled_2fcn", (0.5, 0.5), False, {"set_use_line_search": False}, (5000, 10), 1e-6),        # _2
+    ("newton", "poorly_scaled_2fcn", (1.0, 1.0), False, {"set_use_line_search": False}, (5000, 10), 1e-6),
+    ("newton", "misc_2fcn_a", (0.5, 0.5), False, {}, (5, 3), 1e-6),              # test_newton_3
+    ("newton", "misc_2fcn_a", (1.0, 1.0), True, {}, (5, 3), 1e-6),
+    ("newton", "powell_badly_scaled", (0.0, 1.0), True, {}, (1.098159e-5, 9.106146), 1e-5),                     # test_newton_4
+    ("newton", "misc_2fcn_01", (1.0, 1.0), True, {}, (0.567143, 0.567143), 1e-5),   # examples/nonlin_newton_solve_jacobian.f90
+    ("least_squares", "misc_2fcn", (0.5, 0.5), True, {}, (5, 3), 1e-6),          # test_least_squares_1
+    ("least_squares", "misc_2fcn", (1.0, 1.0), True, {}, (5, 3), 1e-6),
+    ("least_squares", "poorly_scaled_2fcn", (0.5, 0.5), False, {"set_max_fcn_evals": 1000}, (5000, 10), 1e-6),  # _2
+    ("least_squares", "poorly_scaled_2fcn", (1.0, 1.0), False, {"set_max_fcn_evals": 1000}, (5000, 10), 1e-6),
+    ("least_squares", "misc_2fcn", (0.5, 0.5), False, {}, (5, 3), 1e-6),         # test_least_squares_4 (FD then analytic)
+]
+
+
+@pytest.mark.parametrize("case", TABLE, ids=lambda c: "%s-%s-%s-%s" % (c[0], c[1], c[2][0], "jac" if c[3] else "fd"))
+def test_reference_test_table(engine, oracle, case):
+    import nonlin_b200 as nb
+
+    solver, fcn, x0, analytic, settings, expect, tol = case
+    B = 67   # odd size: last block is ragged
+    w = dict(solver=solver, fcn=fcn, m=2, n=2, x0=np.tile(np.array(x0)[:, None], (1, B)).copy(),
+             args=np.full((1, B), 2.0) if fcn == "misc_2fcn_a" else None, shared=None, settings=settings)
+    x, f, ib, st = run_engine(nb, w, analytic=analytic)
+    assert np.all(st == 0)
+    assert np.all(np.abs(np.abs(x) - np.array(expect)[:, None]) <= tol)
+    # every copy is the same bits, and equals the oracle's single solve
+    assert np.all(x == x[:, :1]) and np.all(f == f[:, :1]) and np.all(ib == ib[0])
+    kw = {}
+    if "set_max_fcn_evals" in settings:
+        kw["max_fcn_evals"] = settings["set_max_fcn_evals"]
+    if "set_use_line_search" in settings:
+        kw["use_line_search"] = int(settings["set_use_line_search"])
+    xo, fo, ibo, sto = oracle.solve(solver, fcn, list(x0), sys=[2.0] if fcn == "misc_2fcn_a" else None,
+                                    params=oracle.params(use_analytic_jacobian=int(analytic), **kw))
+    assert sto == 0 and np.array_equal(x[:, 0], xo) and np.array_equal(f[:, 0], fo)
+    assert {k: int(ib[0][k]) for k in ib.dtype.names} == ibo
+
+
+def test_readme_examples_through_the_engine(engine):
+    """README Example 1 (11 / 15 / 1) and Example 2 (10 printed digits) on the GPU."""
+    import nonlin_b200 as nb
+
+    obj = nb.vecfcn_helper(); obj.set_fcn("misc_2fcn", 2, 2)
+    s = nb.quasi_newton_solver()
+    s.set_jacobian_interval(20); s.set_fcn_tolerance(1e-8); s.set_var_tolerance(1e-12); s.set_gradient_tolerance(1e-12)
+    x = np.ones((2, 1)); f = np.zeros((2, 1)); ib = nb.iteration_behavior(1)
+    st = s.solve(obj, x, f, ib)
+    assert st[0] == 0 and ["%.5f" % v for v in x[:, 0]] == ["5.00000", "3.00000"]
+    assert (ib[0]["iter_count"], ib[0]["fcn_count"], ib[0]["jacobian_count"]) == (11, 15, 1)
+    assert "%.3e" % f[0, 0] == "3.233e-12" and "%.3e" % f[1, 0] == "7.052e-12"
+
+    from nonlin_b200.workloads import POLYFIT_YP
+
+    obj = nb.vecfcn_helper(); obj.set_fcn("lsq_poly_fit", 21, 4)
+    x = np.ones((4, 1)); f = np.zeros((21, 1))
+    st = nb.least_squares_solver().solve(obj, x, f, args=POLYFIT_YP[:, None].copy())
+    assert st[0] == 0
+    assert ["%.10f" % v for v in x[::-1, 0]] == ["1.1866142244", "0.4466134462", "-0.1223202909", "1.0647627571"]
+    assert "%.5f" % np.abs(f).max() == "0.50636"
+
+
+# ---------------------------------------------------------------------------------------------
+# failure paths: per-system status instead of `error stop`
+# ---------------------------------------------------------------------------------------------
+def test_status_codes_match_oracle(engine, oracle):
+    import nonlin_b200 as nb
+    from nonlin_b200 import workloads as W
+
+    # default max_fcn_evals = 100 is exhausted by part of the Powell starts
+    w = W.c3_newton_powell(4096)
+    w["settings"] = {}
+    x, f, ib, st = run_engine(nb, w)
+    xo, fo, ibo, sto = oracle.solve_batch("newton", w["fcn"], w["x0"])
+    assert 0 < (sto != 0).mean() < 0.5 and set(np.unique(sto)) <= {0, nb.NL_CONVERGENCE_ERROR}
+    assert np.array_equal(st, sto) and np.array_equal(x, xo) and np.array_equal(f, fo) and np.array_equal(ib, ibo)
+    # LM on the poorly scaled system needs > 100 evaluations
+    w = dict(solver="least_squares", fcn="poorly_scaled_2fcn", m=2, n=2, x0=np.ones((2, 5)), args=None, shared=None, settings={})
+    x, f, ib, st = run_engine(nb, w)
+    assert np.all(st == nb.NL_CONVERGENCE_ERROR) and np.all(ib["fcn_count"] == 100)
+    # starting on the root
+    w = dict(solver="newton", fcn="misc_2fcn", m=2, n=2, x0=np.array([[5.0, -5.0], [3.0, 3.0]]), args=None, shared=None, settings={})
+    x, f, ib, st = run_engine(nb, w)
+    assert np.all(st == 0) and np.all(ib["iter_count"] == 0) and np.all(ib["fcn_count"] == 1) and np.all(ib["converge_on_fcn"] == 1)
+    # singular Jacobian at the origin: same code as the oracle, no hang
+    for solver in ("newton", "quasi_newton", "least_squares"):
+        w = dict(solver=solver, fcn="misc_2fcn", m=2, n=2, x0=np.zeros((2, 3)), args=None, shared=None, settings={})
+        x, f, ib, st = run_engine(nb, w)
+        xo, fo, ibo, sto = oracle.solve(solver, "misc_2fcn", [0.0, 0.0])
+        assert np.all(st == sto)
+        assert {k: int(ib[0][k]) for k in ib.dtype.names} == ibo
+
+
+def test_api_errors(engine):
+    import nonlin_b200 as nb
+
+    obj = nb.vecfcn_helper(); obj.set_fcn("lsq_poly_fit", 21, 4)
+    with pytest.raises(nb.NonlinError) as e:      # m != n for Newton (src/nonlin_solve.f90:519)
+        nb.newton_solver().solve(obj, np.ones((4, 2)), args=np.ones((21, 2)))
+    assert e.value.code == nb.NLB_ERR_SIZE
+    with pytest.raises(nb.NonlinError) as e:      # per-system data missing
+        nb.least_squares_solver().solve(obj, np.ones((4, 2)))
+    assert e.value.code == nb.NLB_ERR_INVALID_ARGUMENT
+    # empty batch is a no-op
+    st = nb.least_squares_solver().solve(obj, np.ones((4, 0)), args=np.ones((21, 0)))
+    assert st.shape == (0,)
+
+
+# ---------------------------------------------------------------------------------------------
+# vecfcn_helper%fcn / %jacobian
+# ---------------------------------------------------------------------------------------------
+def test_fd_jacobian_batch(engine, oracle):
+    import nonlin_b200 as nb
+
+    pts = np.array([[0.0, 1.0, 0.0, 0.5], [0.0, 0.0, 1.0, -0.5]])   # tests/nonlin_test_jacobian.f90:89-177
+    obj = nb.vecfcn_helper(); obj.set_fcn("polar", 2, 2)
+    jac = obj.jacobian(pts)                                           # (n, m, B)
+    for b in range(4):
+        r, th = pts[:, b]
+        exact = np.array([[np.cos(th), -r * np.sin(th)], [np.sin(th), r * np.cos(th)]])
+        assert np.all(np.abs(jac[:, :, b].T - exact) <= 1e-4)
+    obj.set_fcn("polar_scaled", 2, 2)
+    jac2 = obj.jacobian(pts, args=np.full((1, 4), 2.0))
+    assert np.all(np.abs(jac2 - 2.0 * jac) <= 2e-4)
+    obj.set_fcn("polar", 2, 2); obj.set_jacobian()
+    ja = obj.jacobian(pts)
+    assert np.all(np.abs(ja - jac) <= 1e-4)
+    # bitwise against the oracle on a residual made of basic operations only
+    rng = np.random.default_rng(7)
+    B = 1000
+    x = rng.uniform(-3, 3, size=(4, B)); y = rng.standard_normal((21, B))
+    obj.set_fcn("lsq_poly_fit", 21, 4)
+    jac = obj.jacobian(x, args=y)
+    fv = obj.fcn(x, args=y)
+    for b in (0, 1, 499, 999):
+        assert np.array_equal(jac[:, :, b].T, oracle.jacobian("lsq_poly_fit", x[:, b], sys=y[:, b]))
+        assert np.array_equal(fv[:, b], oracle.eval_fcn("lsq_poly_fit", x[:, b], sys=y[:, b]))
+
+
+def test_software_exp_bitwise(engine, oracle):
+    """Residuals calling exp() agree bit for bit (the engine and the oracle carry independent
+    copies of the same basic-operations-only exponential)."""
+    import nonlin_b200 as nb
+
+    rng = np.random.default_rng(11)
+    B = 20000
+    x = np.stack([rng.uniform(-20, 20, B), rng.uniform(-0.5, 12, B)])
+    obj = nb.vecfcn_helper(); obj.set_fcn("powell_badly_scaled", 2, 2)
+    f = obj.fcn(x)
+    fo = np.stack([oracle.eval_fcn("powell_badly_scaled", x[:, b]) for b in range(B)], axis=1)
+    assert np.array_equal(f, fo)
+
+
+# ---------------------------------------------------------------------------------------------
+# host-pointer path == device-pointer path; statistics
+# ---------------------------------------------------------------------------------------------
+def test_host_and_device_buffers_give_the_same_bits(engine):
+    import torch
+
+    import nonlin_b200 as nb
+    from nonlin_b200 import workloads as W
+
+    B = 5000
+    w = W.c1_lm_polyfit(B)
+    x, f, ib, st = run_engine(nb, w)
+    obj = nb.vecfcn_helper(); obj.set_fcn(w["fcn"], w["m"], w["n"])
+    xd = torch.from_numpy(w["x0"]).cuda(); ad = torch.from_numpy(w["args"]).cuda()
+    fd = torch.empty((w["m"], B), dtype=torch.float64, device="cuda")
+    ibd = nb.iteration_behavior(B, like=xd)
+    std = nb.least_squares_solver().solve(obj, xd, fd, ibd, args=ad)
+    torch.cuda.synchronize()
+    assert np.array_equal(xd.cpu().numpy(), x) and np.array_equal(fd.cpu().numpy(), f)
+    assert np.array_equal(nb.ib_view(ibd), ib) and np.array_equal(std.cpu().numpy(), st)
+    stats = engine.reduce_stats(ibd, std, B)
+    assert stats["systems"] == B and stats["converged"] == int((st == 0).sum()) and stats["failed"] == int((st != 0).sum())
+    assert stats["sum_iter"] == int(ib["iter_count"].sum()) and stats["sum_fcn"] == int(ib["fcn_count"].sum())
+    assert stats["sum_jac"] == int(ib["jacobian_count"].sum()) and stats["max_iter"] == int(ib["iter_count"].max())
+    assert stats["converged_fcn"] == int(ib["converge_on_fcn"].sum()) and stats["converged_chng"] == int(ib["converge_on_chng"].sum())
+    assert engine.reduce_stats(ib, st) == stats     # host arrays in, same numbers
+
+
+# ---------------------------------------------------------------------------------------------
+# full BASELINE sizes: size-independent properties
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["C2", "C3", "C1"])
+def test_full_size_properties(engine, oracle, name):
+    """At B = 2^20: (1) every system converges; (2) the reported fvec is F(x) re-evaluated;
+    (3) the roots satisfy the equations to ftol; (4) a system's result does not depend on its
+    position in the batch (solve a permuted batch, un-permute, same bits); (5) a strided sample
+    is bit-identical to the oracle."""
+    import torch
+
+    import nonlin_b200 as nb
+    from nonlin_b200 import workloads as W
+
+    B = 1 << 20
+    w = W.WORKLOADS[name](B)
+    obj = nb.vecfcn_helper(); obj.set_fcn(w["fcn"], w["m"], w["n"])
+    s = make_solver(nb, w)
+    x0 = torch.from_numpy(w["x0"]).cuda()
+    args = None if w["args"] is None else torch.from_numpy(w["args"]).cuda()
+    x = x0.clone(); f = torch.empty((w["m"], B), dtype=torch.float64, device="cuda")
+    ib = nb.iteration_behavior(B, like=x); st = s.solve(obj, x, f, ib, args=args)
+    stats = engine.reduce_stats(ib, st, B)
+    assert stats["systems"] == B and stats["converged"] == B and stats["failed"] == 0
+    f2 = obj.fcn(x, args=args)
+    assert torch.equal(f, f2)
+    if name != "C1":
+        assert float(f.abs().max()) < 1e-8
+    perm = torch.randperm(B, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+    xp = x0[:, perm].contiguous(); ap = None if args is None else args[:, perm].contiguous()
+    fp = torch.empty_like(f); ibp = nb.iteration_behavior(B, like=x)
+    stp = s.solve(obj, xp, fp, ibp, args=ap)
+    assert torch.equal(xp, x[:, perm]) and torch.equal(fp, f[:, perm]) and torch.equal(ibp, ib[perm]) and torch.equal(stp, st[perm])
+    idx = np.arange(0, B, 257)
+    xo, fo, ibo, sto = oracle.solve_batch(w["solver"], w["fcn"], np.ascontiguousarray(w["x0"][:, idx]), m=w["m"],
+                                          sys=None if w["args"] is None else np.ascontiguousarray(w["args"][:, idx]),
+                                          params=oracle_params(oracle, w))
+    assert np.array_equal(x.cpu().numpy()[:, idx], xo) and np.array_equal(f.cpu().numpy()[:, idx], fo)
+    assert np.array_equal(nb.ib_view(ib)[idx], ibo) and np.array_equal(st.cpu().numpy()[idx], sto)

@@ -1,0 +1,101 @@
+"""Host-side mirror of the reference's solver objects: same names, defaults, clamps and error
+behaviour.  CPU only — no solve is launched."""
+import numpy as np
+import pytest
+
+import nonlin_b200 as nb
+
+
+def test_equation_solver_defaults_and_setters():
+    for cls in (nb.least_squares_solver, nb.newton_solver, nb.quasi_newton_solver):
+        s = cls()
+        assert s.get_max_fcn_evals() == 100                      # src/nonlin_multi_eqn_mult_var.f90:69
+        assert s.get_fcn_tolerance() == 1e-8                     # :71
+        assert s.get_var_tolerance() == 1e-12                    # :73
+        assert s.get_gradient_tolerance() == 1e-12               # :75
+        assert s.get_print_status() is False                     # :77
+        s.set_max_fcn_evals(1000); s.set_fcn_tolerance(1e-10); s.set_var_tolerance(1e-9); s.set_gradient_tolerance(1e-7)
+        s.set_print_status(True)
+        assert (s.get_max_fcn_evals(), s.get_fcn_tolerance(), s.get_var_tolerance(), s.get_gradient_tolerance()) == (1000, 1e-10, 1e-9, 1e-7)
+        assert s.get_print_status() is True
+
+
+def test_lm_step_scaling_factor_clamp():
+    s = nb.least_squares_solver()
+    assert s.get_step_scaling_factor() == 100.0                  # src/nonlin_least_squares.f90:25
+    s.set_step_scaling_factor(0.01); assert s.get_step_scaling_factor() == 0.1      # :108-109
+    s.set_step_scaling_factor(1e3); assert s.get_step_scaling_factor() == 100.0     # :110-111
+    s.set_step_scaling_factor(5.0); assert s.get_step_scaling_factor() == 5.0
+
+
+def test_quasi_newton_and_line_search_settings():
+    s = nb.quasi_newton_solver()
+    assert s.get_jacobian_interval() == 5                        # src/nonlin_solve.f90:51
+    s.set_jacobian_interval(20); assert s.get_jacobian_interval() == 20
+    assert s.get_use_line_search() is True and not s.is_line_search_defined()   # :30
+    ls = nb.line_search()
+    assert (ls.get_max_fcn_evals(), ls.get_scaling_factor(), ls.get_distance_factor()) == (100, 1e-4, 0.1)
+    ls.set_distance_factor(-1.0); assert ls.get_distance_factor() == 0.1          # src/nonlin_linesearch.f90:142-143
+    ls.set_distance_factor(2.0); assert ls.get_distance_factor() == 0.99          # :144-145
+    ls.set_distance_factor(0.5); assert ls.get_distance_factor() == 0.5
+    ls.set_max_fcn_evals(7); ls.set_scaling_factor(1e-3)
+    s.set_line_search(ls)
+    assert s.is_line_search_defined() and s.get_line_search() is not ls           # stored as a copy (:103-111)
+    obj = nb.vecfcn_helper(); obj.set_fcn("misc_2fcn", 2, 2)
+    p = s._params(obj)
+    assert (p.jacobian_interval, p.ls_max_fcn_evals, p.ls_alpha, p.ls_factor, p.use_line_search) == (20, 7, 1e-3, 0.5, 1)
+    s.set_use_line_search(False)
+    assert s._params(obj).use_line_search == 0
+    # solve lazily installs a default line search, like the reference (:229-233)
+    s2 = nb.newton_solver()
+    s2._params(obj)
+    assert s2.is_line_search_defined()
+
+
+def test_vecfcn_helper():
+    obj = nb.vecfcn_helper()
+    assert not obj.is_fcn_defined() and not obj.is_jacobian_defined()
+    obj.set_fcn("lsq_poly_fit", 21, 4)
+    assert obj.is_fcn_defined() and (obj.get_equation_count(), obj.get_variable_count()) == (21, 4)
+    with pytest.raises(nb.NonlinError):
+        obj.set_jacobian()                       # no analytic Jacobian registered for this residual
+    with pytest.raises(nb.NonlinError):
+        obj.set_fcn("lsq_poly_fit", 20, 4)       # size mismatch
+    with pytest.raises(nb.NonlinError):
+        obj.set_fcn("not_registered", 2, 2)
+    obj.set_fcn("powell_badly_scaled", 2, 2); obj.set_jacobian()
+    assert obj.is_jacobian_defined()
+    obj.set_fcn("ext_rosenbrock", 64, 64)
+    assert obj.get_variable_count() == 64
+    obj.set_fcn("rational_7_8", 4096, 16)
+    assert obj._info["sys_len"] == 4096 and obj._info["shared_len"] == 4096
+    with pytest.raises(nb.NonlinError):
+        obj.set_fcn("rational_7_8")              # run-time sized family needs m
+
+
+def test_solve_argument_checks_happen_before_any_launch():
+    obj = nb.vecfcn_helper()
+    s = nb.newton_solver()
+    with pytest.raises(nb.NonlinError):          # NL_UNDEFINED_FUNCTION_ERROR analogue
+        s.solve(obj, np.ones((2, 3)))
+    obj.set_fcn("misc_2fcn", 2, 2)
+    with pytest.raises(nb.NonlinError):          # size(x) /= nvar -> error stop 3
+        s.solve(obj, np.ones((3, 3)))
+    with pytest.raises(nb.NonlinError):          # size(fvec) /= neqn -> error stop 4
+        s.solve(obj, np.ones((2, 3)), np.ones((3, 3)))
+    with pytest.raises(TypeError):
+        s.solve(obj, np.ones((2, 3), dtype=np.float32))
+
+
+def test_workloads_are_seeded_and_shaped():
+    from nonlin_b200 import workloads as W
+
+    for name, fn in W.WORKLOADS.items():
+        kw = {"m": 128} if name == "C4" else {}
+        a, b = fn(64, **kw), fn(64, **kw)
+        assert np.array_equal(a["x0"], b["x0"]) and a["x0"].shape == (a["n"], 64)
+        if a["args"] is not None:
+            assert np.array_equal(a["args"], b["args"]) and a["args"].shape[1] == 64
+        assert a["bytes_per_system"] > 0
+    assert W.c1_lm_polyfit(1)["bytes_per_system"] == 432 and W.c2_broyden_2x2(1)["bytes_per_system"] == 80
+    assert W.c5_broyden_rosenbrock(1)["bytes_per_system"] == 1568

@@ -1,0 +1,37 @@
+// README Example 1 of the reference (examples/nonlin_quasi_newton_example.f90) through the C++ host
+// mirror, B copies.  Built and run by tests/test_gpu_parity.py::test_cxx_host_mirror on the GPU box;
+// compiled (not run) by tests/test_abi.py on CPU.
+#include <cstdio>
+#include <vector>
+
+#include "../nonlin_b200/host/nonlin_batch.hpp"
+
+int main() {
+    const int64_t B = 1000;
+    try {
+        nonlin::engine eng(0);
+        nonlin::vecfcn_helper obj;
+        obj.set_fcn("misc_2fcn", 2, 2);
+        nonlin::quasi_newton_solver solver;
+        solver.set_jacobian_interval(20);
+        solver.set_fcn_tolerance(1.0e-8);
+        solver.set_var_tolerance(1.0e-12);
+        solver.set_gradient_tolerance(1.0e-12);
+        std::vector<double> x(2 * B, 1.0), f(2 * B);
+        std::vector<nonlin::iteration_behavior> ib(B);
+        std::vector<int32_t> status(B);
+        solver.solve(eng, obj, B, x.data(), f.data(), ib.data(), status.data());
+        for (int64_t b = 0; b < B; ++b) {
+            if (status[b] != 0 || ib[b].iter_count != 11 || ib[b].fcn_count != 15 || ib[b].jacobian_count != 1) {
+                std::printf("FAIL at %lld\n", (long long)b);
+                return 1;
+            }
+        }
+        std::printf("Solution: (%.5f, %.5f)\nResidual: (%.3e, %.3e)\nIterations: %d\nFunction Evaluations: %d\nJacobian Evaluations: %d\n",
+                    x[0], x[B], f[0], f[B], ib[0].iter_count, ib[0].fcn_count, ib[0].jacobian_count);
+    } catch (const nonlin::error& e) {
+        std::printf("nonlin error %d: %s\n", e.code, e.what());
+        return 2;
+    }
+    return 0;
+}

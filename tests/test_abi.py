@@ -101,3 +101,47 @@ def test_product_does_not_touch_the_oracle():
                 if fn.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".f90")):
                     src = open(os.path.join(dirpath, fn)).read()
                     assert "nl_oracle" not in src and "oracle/" not in src and "import oracle" not in src, fn
+
+
+def _build_cxx_example(tmp_path):
+    import subprocess
+
+    exe = str(tmp_path / "cxx_host_example")
+    libdir = os.path.join(ROOT, "nonlin_b200")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-std=c++17", "-O2", "-o", exe, os.path.join(ROOT, "tests", "cxx_host_example.cpp"),
+                           "-L" + libdir, "-lnonlin_b200", "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_cxx_host_mirror_links_against_the_c_abi(tmp_path):
+    """The header-only C++ mirror of the reference's solver objects compiles and links against the
+    C ABI with a plain host compiler (no nvcc, no torch)."""
+    import subprocess
+
+    import torch
+
+    exe = _build_cxx_example(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stdout
+    else:
+        assert r.returncode == 2 and "no usable CUDA device" in r.stdout
+
+
+def test_fortran_binding_declares_every_solver_entry_point():
+    """fortran/nonlin_batch.f90 cannot be compiled here (no Fortran compiler); check at least that its
+    bind(C) names exist in the library and that the interoperable types have the header's field order."""
+    from nonlin_b200 import _lib
+
+    src = open(os.path.join(ROOT, "fortran", "nonlin_batch.f90")).read()
+    names = set(re.findall(r'bind\(C, name = "(nlb_\w+)"\)', src))
+    assert {"nlb_create", "nlb_destroy", "nlb_least_squares_solve_batch", "nlb_newton_solve_batch",
+            "nlb_quasi_newton_solve_batch", "nlb_jacobian_batch", "nlb_reduce_stats"} <= names
+    lib = C.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n)
+    fields = [f[0] for f in _lib.nlb_params._fields_]
+    block = src[src.index("type, bind(C) :: nlb_params"):src.index("end type")]
+    pos = [block.index(f) for f in fields]
+    assert pos == sorted(pos)

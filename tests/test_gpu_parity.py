@@ -331,3 +331,16 @@ def test_full_size_properties(engine, oracle, name):
                                           params=oracle_params(oracle, w))
     assert np.array_equal(x.cpu().numpy()[:, idx], xo) and np.array_equal(f.cpu().numpy()[:, idx], fo)
     assert np.array_equal(nb.ib_view(ib)[idx], ibo) and np.array_equal(st.cpu().numpy()[idx], sto)
+
+
+def test_cxx_host_mirror(engine, tmp_path):
+    """README Example 1 through nonlin_b200/host/nonlin_batch.hpp (C++ over the C ABI, host buffers)."""
+    import subprocess
+
+    from test_abi import _build_cxx_example
+
+    exe = _build_cxx_example(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Solution: (5.00000, 3.00000)" in r.stdout
+    assert "Iterations: 11" in r.stdout and "Function Evaluations: 15" in r.stdout and "Jacobian Evaluations: 1" in r.stdout

@@ -1,0 +1,477 @@
+// coop_broyden.cuh — CTA-per-system Broyden quasi-Newton for mid-size square systems
+// (BASELINE config 5: extended Rosenbrock, n = 64, quasi_newton_solver + line search).
+//
+// Behaviour reproduced: qns_solve, reference src/nonlin_solve.f90:156-425, with its linalg
+// calls (qr_factor, rank1_update, qr_rank1_update, mtx_mult, solve_triangular_system,
+// recip_mult_array) as the Reference-LAPACK / QRUPDATE algorithms listed in tps_dense.cuh.
+//
+// Mapping.  One CTA of N threads owns one system for its whole solve.  B, Q and R (N x N,
+// column-major, leading dimension N+1 so that both row-wise and column-wise sweeps are bank-
+// conflict free) and every vector live in shared memory: 3*N*(N+1)*8 B = 97.5 KB at N = 64,
+// two CTAs per SM.  HBM is touched once to read x0 and once to write x, fvec, ib, status.
+//
+// Parity.  Every sum keeps the index order of the reference's loop, so results are bit-identical
+// to the CPU oracle.  That is affordable because the O(n^2) kernels parallelise over the
+// *other* index: thread t owns output t (a row of B*dx, a column of B^T f / Q^T u / the
+// Householder update, a row of the Q rotations, a column of the R sweeps) and walks its sum
+// sequentially.  The O(n) reductions (dot products, norms, max-norm tests, the Givens chain of
+// DQRTV1) are evaluated redundantly by every thread from the same shared-memory operands,
+// which keeps all scalars and the control flow uniform without broadcasts.
+#pragma once
+#include "tps_common.cuh"
+
+namespace nlb {
+
+template <int N>
+struct CoopBroydenSmem {
+    static constexpr int LD = N + 1;
+    static constexpr int MAT = N * LD;
+    static constexpr int NVEC = 14;
+    static constexpr size_t BYTES = (3 * (size_t)MAT + NVEC * (size_t)N) * sizeof(double);
+};
+
+// ---- redundant sequential reductions (identical in every thread) -----------------------
+template <int N>
+NLB_DEV double cb_dot(const double* a, const double* b) {
+    double s = 0.0;
+#pragma unroll 8
+    for (int i = 0; i < N; ++i) s += a[i] * b[i];
+    return s;
+}
+template <int N>
+NLB_DEV double cb_norm2(const double* a) {
+    Norm2 acc;
+    for (int i = 0; i < N; ++i) acc.add(a[i]);
+    return acc.value();
+}
+template <int N>
+NLB_DEV double cb_maxabs(const double* a) {
+    double t = 0.0;
+    for (int i = 0; i < N; ++i) t = nl_max(fabs(a[i]), t);
+    return t;
+}
+
+// DLARF('L'): H = I - tau v v^T with v = column i of a (a(i,i) == 1) applied to columns c > i.
+// Thread c owns column c: sequential dot over the rows, then its own rank-1 update.
+template <int N>
+NLB_DEV void cb_reflect_trailing(double* a, int i, double tau, int tid) {
+    constexpr int LD = N + 1;
+    if (tau == 0.0) return;
+    int lastv = N - i;                                   // DLARF's scan for trailing zeros of v
+    while (lastv > 0 && a[(i + lastv - 1) + i * LD] == 0.0) --lastv;
+    if (lastv <= 0) return;
+    if (tid > i) {
+        const double* v = a + i + i * LD;
+        double* c = a + i + tid * LD;
+        double temp = 0.0;
+        for (int r = 0; r < lastv; ++r) temp += c[r] * v[r];
+        const double w = 0.0 + 1.0 * temp;
+        if (w != 0.0) {
+            const double t = (-tau) * w;
+            for (int r = 0; r < lastv; ++r) c[r] = c[r] + v[r] * t;
+        }
+    }
+}
+
+// qr_factor(b, q = q, r = r): DGEQR2 on a copy of B, R = upper triangle, Q by DORG2R.
+template <int N>
+NLB_DEV void cb_qr_full(const double* bm, double* q, double* r, double* tau, int tid) {
+    constexpr int LD = N + 1;
+    for (int j = 0; j < N; ++j) q[tid + j * LD] = bm[tid + j * LD];
+    __syncthreads();
+    for (int i = 0; i < N; ++i) {
+        // DLARFG on column i (every thread evaluates the same scalars)
+        double t = 0.0, beta = 0.0, sc = 0.0;
+        bool scale = false;
+        if (N - i > 1) {
+            Dnrm2 acc;
+            for (int rr = i + 1; rr < N; ++rr) acc.add(q[rr + i * LD]);
+            double xnorm = acc.value();
+            if (xnorm != 0.0) {
+                double alpha = q[i + i * LD];
+                beta = -nl_sign(dlapy2(alpha, xnorm), alpha);
+                const double safmin = 0x1p-969;
+                int knt = 0;
+                if (fabs(beta) < safmin) {               // rare: rescale until beta is representable
+                    const double rsafmn = 1.0 / safmin;
+                    do {
+                        ++knt;
+                        __syncthreads();
+                        if (tid > i) q[tid + i * LD] = rsafmn * q[tid + i * LD];
+                        __syncthreads();
+                        beta = beta * rsafmn;
+                        alpha = alpha * rsafmn;
+                    } while (fabs(beta) < safmin && knt < 20);
+                    Dnrm2 acc2;
+                    for (int rr = i + 1; rr < N; ++rr) acc2.add(q[rr + i * LD]);
+                    xnorm = acc2.value();
+                    beta = -nl_sign(dlapy2(alpha, xnorm), alpha);
+                }
+                t = (beta - alpha) / beta;
+                sc = 1.0 / (alpha - beta);
+                scale = true;
+                for (int k = 0; k < knt; ++k) beta = beta * safmin;
+            }
+        }
+        __syncthreads();                                 // all reads of column i done
+        if (scale) {
+            if (tid > i) q[tid + i * LD] = sc * q[tid + i * LD];
+            if (tid == i) q[i + i * LD] = beta;
+        }
+        if (tid == 0) tau[i] = t;
+        __syncthreads();
+        if (i < N - 1) {
+            const double aii = q[i + i * LD];
+            __syncthreads();
+            if (tid == i) q[i + i * LD] = 1.0;
+            __syncthreads();
+            cb_reflect_trailing<N>(q, i, t, tid);
+            __syncthreads();
+            if (tid == i) q[i + i * LD] = aii;
+            __syncthreads();
+        }
+    }
+    for (int j = 0; j < N; ++j) r[tid + j * LD] = (tid <= j) ? q[tid + j * LD] : 0.0;
+    __syncthreads();
+    // DORG2R
+    for (int i = N - 1; i >= 0; --i) {
+        const double t = tau[i];
+        if (i < N - 1) {
+            if (tid == i) q[i + i * LD] = 1.0;
+            __syncthreads();
+            cb_reflect_trailing<N>(q, i, t, tid);
+            __syncthreads();
+            if (tid > i) q[tid + i * LD] = (-t) * q[tid + i * LD];
+        }
+        if (tid == i) q[i + i * LD] = 1.0 - t;
+        if (tid < i) q[tid + i * LD] = 0.0;
+        __syncthreads();
+    }
+}
+
+// DQR1UP (full Q): Q R + u v^T -> Q1 R1.  w, cs, sn: N-entry shared work vectors.
+template <int N>
+NLB_DEV void cb_qr_rank1_update(double* q, double* r, const double* u, const double* v, double* w, double* cs,
+                                double* sn, int tid) {
+    constexpr int LD = N + 1;
+    // w = Q^T u : thread t owns column t of Q
+    {
+        double s = 0.0;
+        const double* qc = q + tid * LD;
+#pragma unroll 8
+        for (int l = 0; l < N; ++l) s += qc[l] * u[l];
+        w[tid] = s;
+    }
+    __syncthreads();
+    // DQRTV1: the Givens chain that folds w into w(1), bottom-up (strictly sequential)
+    double w0;
+    {
+        double rr = w[N - 1];
+        for (int i = N - 2; i >= 0; --i) {
+            double c, s, t;
+            dlartg(w[i], rr, c, s, t);
+            if (tid == 0) { cs[i] = c; sn[i] = s; }
+            rr = t;
+        }
+        w0 = rr;
+    }
+    __syncthreads();
+    // DQRQH: R -> upper Hessenberg, thread t owns column t
+    {
+        double* rc = r + tid * LD;
+        const int ii = (N - 2 < tid) ? N - 2 : tid;
+        double t = rc[ii + 1];
+        for (int j = ii; j >= 0; --j) {
+            const double c = cs[j], s = sn[j], rj = rc[j];
+            rc[j + 1] = c * t - s * rj;
+            t = c * rj + s * t;
+        }
+        rc[0] = t;
+    }
+    // DQROT('B'): Q <- Q G^T, last rotation first; thread t owns row t
+    {
+        double hi = q[tid + (N - 1) * LD];
+        for (int i = N - 2; i >= 0; --i) {
+            const double c = cs[i], s = sn[i], lo = q[tid + i * LD];
+            const double t = c * lo + s * hi;
+            q[tid + (i + 1) * LD] = c * hi - s * lo;
+            hi = t;
+        }
+        q[tid] = hi;
+    }
+    __syncthreads();
+    // first row of R += w(1) v^T
+    r[tid * LD] = r[tid * LD] + w0 * v[tid];
+    __syncthreads();
+    // DQHQR: back to triangular.  Rotation j is generated from column j once rotations 0..j-1
+    // have been applied to it, then applied to the columns to its right.
+    {
+        double* rc = r + tid * LD;
+        double t = rc[0];
+        for (int j = 0; j < N - 1; ++j) {
+            if (tid == j) {
+                double c, s, rjj;
+                dlartg(t, rc[j + 1], c, s, rjj);
+                cs[j] = c; sn[j] = s;
+                rc[j] = rjj;
+                rc[j + 1] = 0.0;
+            }
+            __syncthreads();
+            if (tid > j) {
+                const double c = cs[j], s = sn[j], rn = rc[j + 1];
+                rc[j] = c * t + s * rn;
+                t = c * rn - s * t;
+            }
+        }
+        if (tid == N - 1) rc[N - 1] = t;
+    }
+    // DQROT('F')
+    {
+        double lo = q[tid];
+        for (int i = 0; i < N - 1; ++i) {
+            const double c = cs[i], s = sn[i], hi = q[tid + (i + 1) * LD];
+            q[tid + i * LD] = c * lo + s * hi;
+            lo = c * hi - s * lo;
+        }
+        q[tid + (N - 1) * LD] = lo;
+    }
+    __syncthreads();
+}
+
+// Residual interface for this kernel: F::component(x, i, n, ctx) = f_i(x), x in shared memory.
+struct ExtRosenbrockCoop {
+    static constexpr int ID = FCN_EXT_ROSENBROCK;
+    NLB_DEV static double component(const double* x, int i, int, const SysCtx&) { return ExtRosenbrock::component(x, i); }
+};
+
+template <class F, int N>
+__global__ void __launch_bounds__(N)
+coop_broyden_kernel(DevParams p, long long B, double* __restrict__ xg, double* __restrict__ fg,
+                    const double* __restrict__ sys, const double* __restrict__ shared,
+                    nlb_iteration_behavior* __restrict__ ibg, int32_t* __restrict__ statusg) {
+    using S = CoopBroydenSmem<N>;
+    constexpr int LD = S::LD;
+    extern __shared__ double smem[];
+    double* bm = smem;
+    double* q = bm + S::MAT;
+    double* r = q + S::MAT;
+    double* x = r + S::MAT;
+    double* fvec = x + N;
+    double* xold = fvec + N;
+    double* fvold = xold + N;
+    double* dx = fvold + N;
+    double* df = dx + N;
+    double* s = df + N;
+    double* w = s + N;
+    double* cs = w + N;
+    double* sn = cs + N;
+    double* tau = sn + N;
+    double* xp = tau + N;     // perturbed copy of x for the forward differences
+    const int tid = threadIdx.x;
+    const long long b = blockIdx.x;
+    if (b >= B) return;
+    SysCtx c{sys ? sys + b : nullptr, shared, B, N, N};
+
+    const double ftol = p.fcn_tol, xtol = p.var_tol, gtol = p.grad_tol;
+    bool restart = true, xcnvrg = false, fcnvrg = false, gcnvrg = false;
+    int neval = 0, iter = 0, njac = 0, flag = 0, jcount = 0, status = NLB_NO_ERROR;
+
+    x[tid] = xg[(long long)tid * B + b];
+    __syncthreads();
+    fvec[tid] = F::component(x, tid, N, c);
+    __syncthreads();
+    double f = 0.5 * cb_dot<N>(fvec, fvec);
+    ++neval;
+    if (cb_maxabs<N>(fvec) < ftol) fcnvrg = true;
+
+    if (!fcnvrg) {
+        const double stpmax = 100.0 * nl_max(cb_norm2<N>(x), (double)N);
+        double fold = f;
+        for (;;) {
+            ++iter;
+            if (iter > p.max_iter_guard) { flag = 1; break; }
+            if (restart) {
+                // forward-difference Jacobian, column by column (vfh_jac_fcn :262-275)
+                xp[tid] = x[tid];
+                __syncthreads();
+                const double eps = 0x1p-26;
+                for (int j = 0; j < N; ++j) {
+                    const double temp = x[j];
+                    double h = eps * fabs(temp);
+                    if (h == 0.0) h = eps;
+                    if (tid == 0) xp[j] = temp + h;
+                    __syncthreads();
+                    const double f1 = F::component(xp, tid, N, c);
+                    bm[tid + j * LD] = (f1 - fvec[tid]) / h;
+                    __syncthreads();
+                    if (tid == 0) xp[j] = temp;
+                }
+                ++njac;
+                __syncthreads();
+                cb_qr_full<N>(bm, q, r, tau, tid);
+                jcount = 0;
+            } else {
+                df[tid] = fvec[tid] - fvold[tid];
+                dx[tid] = x[tid] - xold[tid];
+                __syncthreads();
+                const double x2 = cb_dot<N>(dx, dx);
+                {   // s = df - matmul(b, dx): row t accumulates over j from zero
+                    double acc = 0.0;
+#pragma unroll 8
+                    for (int j = 0; j < N; ++j) acc = acc + bm[tid + j * LD] * dx[j];
+                    double sv = df[tid] - acc;
+                    // recip_mult_array (DRSCL)
+                    const double smlnum = 0x1p-1022, bignum = 1.0 / smlnum;
+                    double cden = x2, cnum = 1.0;
+                    for (;;) {
+                        const double cden1 = cden * smlnum, cnum1 = cnum / bignum;
+                        double mul;
+                        bool done;
+                        if (fabs(cden1) > fabs(cnum) && cnum != 0.0) { mul = smlnum; done = false; cden = cden1; }
+                        else if (fabs(cnum1) > fabs(cden)) { mul = bignum; done = false; cnum = cnum1; }
+                        else { mul = cnum / cden; done = true; }
+                        sv = mul * sv;
+                        if (done) break;
+                    }
+                    s[tid] = sv;
+                    // rank1_update (DGER, alpha = 1): row t of B
+                    for (int j = 0; j < N; ++j) {
+                        const double dj = dx[j];
+                        if (dj != 0.0) bm[tid + j * LD] = bm[tid + j * LD] + sv * (1.0 * dj);
+                    }
+                }
+                __syncthreads();
+                cb_qr_rank1_update<N>(q, r, s, dx, w, cs, sn, tid);
+                ++jcount;
+            }
+
+            // gradient B^T F -> dx ; save state ; -Q^T F -> df
+            {
+                double t1 = 0.0, t2 = 0.0;
+                const double* bc = bm + tid * LD;
+                const double* qc = q + tid * LD;
+#pragma unroll 8
+                for (int i = 0; i < N; ++i) t1 += bc[i] * fvec[i];
+#pragma unroll 8
+                for (int i = 0; i < N; ++i) t2 += qc[i] * fvec[i];
+                __syncthreads();          // everyone is done reading dx / df of the update step
+                dx[tid] = 0.0 + 1.0 * t1;
+                df[tid] = 0.0 + (-1.0) * t2;
+                xold[tid] = x[tid];
+                fvold[tid] = fvec[tid];
+            }
+            fold = f;
+            __syncthreads();
+            // R step = -Q^T F (DTRSV upper, no-trans, non-unit)
+            for (int j = N - 1; j >= 0; --j) {
+                const double xj = df[j];
+                if (xj != 0.0) {
+                    const double t = xj / r[j + j * LD];
+                    __syncthreads();
+                    if (tid < j) df[tid] = df[tid] - t * r[tid + j * LD];
+                    if (tid == j) df[j] = t;
+                }
+                __syncthreads();
+            }
+
+            double temp = cb_dot<N>(dx, df);
+            if (temp >= 0.0) { restart = true; continue; }
+
+            if (p.use_line_search) {
+                temp = cb_dot<N>(df, df);
+                __syncthreads();
+                if (temp > stpmax) df[tid] = df[tid] * (stpmax / temp);
+                __syncthreads();
+                {   // limit_search_vector
+                    const double mag = cb_norm2<N>(df);
+                    __syncthreads();
+                    if (mag != 0.0 && mag > stpmax) df[tid] = (stpmax / mag) * df[tid];
+                    __syncthreads();
+                }
+                // ls_search_mimo
+                int ls_status = NLB_NO_ERROR, ls_eval = 0, niter = 0;
+                const double slope = cb_dot<N>(dx, df);
+                if (slope >= 0.0) {
+                    ls_status = NLB_DIVERGENT_BEHAVIOR_ERROR;
+                    f = 0.0;
+                } else {
+                    double test = 0.0;
+                    for (int i = 0; i < N; ++i) {
+                        const double tt = fabs(df[i]) / nl_max(fabs(xold[i]), 1.0);
+                        if (tt > test) test = tt;
+                    }
+                    const double alamin = 0x1p-51 / test;
+                    double alam = 1.0, alam1 = 0.0, f1 = 0.0, tmplam = 0.0;
+                    for (;;) {
+                        x[tid] = xold[tid] + alam * df[tid];
+                        __syncthreads();
+                        fvec[tid] = F::component(x, tid, N, c);
+                        __syncthreads();
+                        f = 0.5 * cb_dot<N>(fvec, fvec);
+                        ++ls_eval;
+                        ++niter;
+                        if (alam < alamin) {
+                            bool same = true;
+                            for (int i = 0; i < N; ++i) same = same && ((x[i] - xold[i]) == 0.0);
+                            if (same) { ls_status = NLB_CONVERGENCE_ERROR; break; }
+                            __syncthreads();
+                            x[tid] = xold[tid];
+                            __syncthreads();
+                            break;
+                        } else if (f <= fold + p.ls_alpha * alam * slope) {
+                            break;
+                        } else {
+                            tmplam = backtrack_min(niter, fold, f, f1, alam, alam1, slope);
+                        }
+                        alam1 = alam;
+                        f1 = f;
+                        alam = nl_max(tmplam, p.ls_factor * alam);
+                        if (ls_eval >= p.ls_max_fcn_evals) { ls_status = NLB_CONVERGENCE_ERROR; break; }
+                        __syncthreads();
+                    }
+                }
+                neval += ls_eval;
+                if (ls_status != NLB_NO_ERROR) { status = ls_status; break; }
+            } else {
+                x[tid] = x[tid] + df[tid];
+                __syncthreads();
+                fvec[tid] = F::component(x, tid, N, c);
+                __syncthreads();
+                f = 0.5 * cb_dot<N>(fvec, fvec);
+                ++neval;
+            }
+
+            // test_convergence(x, xold, fvec, dx, lg = .false.)
+            bool check = false;
+            xcnvrg = false; fcnvrg = false; gcnvrg = false;
+            if (cb_maxabs<N>(fvec) < ftol) { fcnvrg = true; check = true; }
+            else {
+                double xnorm = 0.0;
+                for (int i = 0; i < N; ++i) {
+                    const double tt = fabs(x[i] - xold[i]) / nl_max(fabs(x[i]), 1.0);
+                    xnorm = nl_max(tt, xnorm);
+                }
+                if (xnorm < xtol) { xcnvrg = true; check = true; }
+            }
+            (void)gtol;
+            if (check) break;
+            restart = (jcount >= p.jacobian_interval);
+            if (neval >= p.max_fcn_evals) { flag = 1; break; }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    xg[(long long)tid * B + b] = x[tid];
+    fg[(long long)tid * B + b] = fvec[tid];
+    if (tid == 0) {
+        if (ibg) {
+            nlb_iteration_behavior o;
+            o.iter_count = iter; o.fcn_count = neval; o.jacobian_count = njac; o.gradient_count = 0;
+            o.converge_on_fcn = fcnvrg; o.converge_on_chng = xcnvrg; o.converge_on_zero_diff = gcnvrg;
+            ibg[b] = o;
+        }
+        if (statusg) statusg[b] = status != NLB_NO_ERROR ? status : (flag != 0 ? NLB_CONVERGENCE_ERROR : NLB_NO_ERROR);
+    }
+}
+
+}  // namespace nlb

@@ -1,15 +1,123 @@
-// coop_kernels.cu — warp- / CTA-per-system kernels (run-time sized residual families).
+// coop_kernels.cu — launchers of the CTA-per-system kernels (run-time sized residual families).
 #include "coop_kernels.cuh"
+
+#include "coop_broyden.cuh"
+#include "coop_lm.cuh"
 
 namespace nlb {
 
-int launch_coop_solve(int, int, const DevParams&, long long, int, int, double*, double*, const double*, const double*,
-                      nlb_iteration_behavior*, int32_t*, cudaStream_t, int64_t*) {
+namespace {
+
+enum { SOLVER_LM = 0, SOLVER_NEWTON = 1, SOLVER_BROYDEN = 2 };
+
+template <class F, int N>
+int launch_broyden(const DevParams& p, long long B, double* x, double* fvec, const double* sys, const double* shared,
+                   nlb_iteration_behavior* ib, int32_t* status, cudaStream_t s, int64_t* launches) {
+    using S = CoopBroydenSmem<N>;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(coop_broyden_kernel<F, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES) !=
+            cudaSuccess)
+            return NLB_ERR_CUDA;
+        configured = true;
+    }
+    coop_broyden_kernel<F, N><<<(unsigned)B, N, S::BYTES, s>>>(p, B, x, fvec, sys, shared, ib, status);
+    ++*launches;
+    return cudaGetLastError() == cudaSuccess ? NLB_OK : NLB_ERR_CUDA;
+}
+
+// one thread per (system, observation): residual of a curve-fit model
+template <class F>
+__global__ void curvefit_eval_kernel(long long B, int m, const double* __restrict__ x, double* __restrict__ fvec,
+                                     const double* __restrict__ sys, const double* __restrict__ shared) {
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double xl[F::N];
+#pragma unroll
+    for (int j = 0; j < F::N; ++j) xl[j] = x[j * B + b];
+    for (int i = blockIdx.y; i < m; i += gridDim.y) fvec[(long long)i * B + b] = F::residual(xl, __ldg(shared + i), sys[(long long)i * B + b]);
+}
+
+__global__ void rosenbrock_eval_kernel(long long B, int n, const double* __restrict__ x, double* __restrict__ fvec) {
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    for (int i = blockIdx.y * 2; i + 1 < n; i += gridDim.y * 2) {
+        const double x0 = x[(long long)i * B + b], x1 = x[(long long)(i + 1) * B + b];
+        fvec[(long long)i * B + b] = 10.0 * (x1 - x0 * x0);
+        fvec[(long long)(i + 1) * B + b] = 1.0 - x0;
+    }
+}
+
+template <class F, int N>
+int launch_lm(const DevParams& p, long long B, int m, double* x, double* fvec, const double* sys, const double* shared,
+              nlb_iteration_behavior* ib, int32_t* status, cudaStream_t s, int64_t* launches) {
+    using S = CoopLmSmem<N>;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(coop_lm_kernel<F, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES) != cudaSuccess)
+            return NLB_ERR_CUDA;
+        configured = true;
+    }
+    // HBM workspace: (n + 2) * m doubles per system, allocated stream-ordered and capped at 8 GiB
+    // per launch; larger batches run as consecutive launches over contiguous system ranges.
+    const size_t per_sys = (size_t)(N + 2) * (size_t)m * sizeof(double);
+    long long chunk = (long long)((8ull << 30) / per_sys) / 32 * 32;
+    if (chunk < 32) chunk = 32;
+    if (chunk > B) chunk = (B + 31) / 32 * 32;
+    double* ws = nullptr;
+    if (cudaMallocAsync((void**)&ws, per_sys * (size_t)chunk, s) != cudaSuccess) return NLB_ERR_CUDA;
+    for (long long b0 = 0; b0 < B; b0 += chunk) {
+        const long long nsys = (B - b0 < chunk) ? (B - b0) : chunk;
+        const unsigned grid = (unsigned)((nsys + 31) / 32);
+        coop_lm_kernel<F, N><<<grid, 32 * N, S::BYTES, s>>>(p, B, b0, nsys, m, x, fvec, sys, shared, ib, status, ws);
+        ++*launches;
+        if (cudaGetLastError() != cudaSuccess) { cudaFreeAsync(ws, s); return NLB_ERR_CUDA; }
+    }
+    if (cudaFreeAsync(ws, s) != cudaSuccess) return NLB_ERR_CUDA;
+    return NLB_OK;
+}
+
+}  // namespace
+
+int launch_coop_lm(int fcn_id, const DevParams& p, long long B, int m, int n, double* x, double* fvec, const double* sys,
+                   const double* shared, nlb_iteration_behavior* ib, int32_t* status, cudaStream_t s, int64_t* launches) {
+    if (m < n) return NLB_ERR_UNSUPPORTED;
+    switch (fcn_id) {
+        case FCN_RATIONAL_7_8: return launch_lm<Rational78, 16>(p, B, m, x, fvec, sys, shared, ib, status, s, launches);
+        case FCN_EXP_SUM_8: return launch_lm<ExpSum8, 16>(p, B, m, x, fvec, sys, shared, ib, status, s, launches);
+        case FCN_EXP_DECAY_4: return launch_lm<ExpDecay4, 4>(p, B, m, x, fvec, sys, shared, ib, status, s, launches);
+        default: return NLB_ERR_UNSUPPORTED;
+    }
+}
+
+int launch_coop_solve(int solver, int fcn_id, const DevParams& p, long long B, int m, int n, double* x, double* fvec,
+                      const double* sys, const double* shared, nlb_iteration_behavior* ib, int32_t* status,
+                      cudaStream_t s, int64_t* launches) {
+    if (solver == SOLVER_BROYDEN && fcn_id == FCN_EXT_ROSENBROCK) {
+        switch (n) {
+            case 8: return launch_broyden<ExtRosenbrockCoop, 8>(p, B, x, fvec, sys, shared, ib, status, s, launches);
+            case 16: return launch_broyden<ExtRosenbrockCoop, 16>(p, B, x, fvec, sys, shared, ib, status, s, launches);
+            case 32: return launch_broyden<ExtRosenbrockCoop, 32>(p, B, x, fvec, sys, shared, ib, status, s, launches);
+            case 64: return launch_broyden<ExtRosenbrockCoop, 64>(p, B, x, fvec, sys, shared, ib, status, s, launches);
+            default: return NLB_ERR_UNSUPPORTED;
+        }
+    }
+    if (solver == SOLVER_LM) return launch_coop_lm(fcn_id, p, B, m, n, x, fvec, sys, shared, ib, status, s, launches);
     return NLB_ERR_UNSUPPORTED;
 }
 
-int launch_coop_eval(int, long long, int, int, const double*, double*, const double*, const double*, cudaStream_t) {
-    return NLB_ERR_UNSUPPORTED;
+int launch_coop_eval(int fcn_id, long long B, int m, int n, const double* x, double* fvec, const double* sys,
+                     const double* shared, cudaStream_t s) {
+    const unsigned gx = (unsigned)((B + 127) / 128);
+    const dim3 grid(gx, (unsigned)(m < 64 ? m : 64));
+    switch (fcn_id) {
+        case FCN_RATIONAL_7_8: curvefit_eval_kernel<Rational78><<<grid, 128, 0, s>>>(B, m, x, fvec, sys, shared); break;
+        case FCN_EXP_SUM_8: curvefit_eval_kernel<ExpSum8><<<grid, 128, 0, s>>>(B, m, x, fvec, sys, shared); break;
+        case FCN_EXP_DECAY_4: curvefit_eval_kernel<ExpDecay4><<<grid, 128, 0, s>>>(B, m, x, fvec, sys, shared); break;
+        case FCN_EXT_ROSENBROCK: rosenbrock_eval_kernel<<<dim3(gx, (unsigned)(n / 2 < 32 ? n / 2 : 32)), 128, 0, s>>>(B, n, x, fvec); break;
+        default: return NLB_ERR_UNSUPPORTED;
+    }
+    return NLB_OK;
 }
 
 }  // namespace nlb

@@ -1,0 +1,562 @@
+// coop_lm.cuh — Levenberg-Marquardt for tall curve fits with run-time m (BASELINE config 4:
+// m = 4096, n = 16; also the 4-parameter fits with m = 64).
+//
+// Behaviour reproduced: lss_solve / lmpar / lmfactor / lmsolve, reference
+// src/nonlin_least_squares.f90:118-391 / 394-566 / 569-667 / 670-791, and the forward-difference
+// Jacobian vfh_jac_fcn, src/nonlin_multi_eqn_mult_var.f90:198-277.
+//
+// Mapping.  A CTA owns 32 systems.  Thread (lane, k) = (system, Jacobian column): warp k holds
+// column k of 32 different systems.  The m x n Jacobian (512 KB per system at C4 — it fits neither
+// shared memory nor registers) lives in an HBM workspace laid out [group][row][column][lane], so a
+// warp reads 256 contiguous bytes per row and the 16 warps of a CTA stream 4 KB-contiguous rows.
+// The two m-vectors (fvec, wa4) use [group][row][lane].  Everything of size n or n x n (R, diag,
+// qtf, the LM work vectors, pivots, per-system scalars and state) is in shared memory, [element]
+// [lane], conflict-free.
+//
+// Parity.  Every m-length sum is walked sequentially by ONE thread in the reference's index
+// order (thread k sums its own column: column norms, the Householder dot products, the FD
+// differences), so the result is bit-identical to the CPU oracle; the parallelism comes from the
+// n columns and from the 32 systems per warp, not from splitting a sum.  Column pivoting is a
+// permutation table (ipvt / pos) instead of a physical swap — same values, no data movement.
+// Row-wise elementwise passes (residual evaluation, wa4 += a(:,j)*temp, copies) are split over
+// the n threads of a system.  The n-sized serial parts (lmpar, lmsolve, gain ratio) run on warp 0.
+//
+// Systems advance in lock step through the phases below (CTA barriers in uniform control flow);
+// a system that is retrying a rejected step idles through the Jacobian/QR phases of its
+// neighbours, a finished system idles until the whole CTA is done (refilling finished lanes from
+// a work queue is the next step).
+#pragma once
+#include "tps_common.cuh"
+
+namespace nlb {
+
+enum { CLM_NEED_JAC = 0, CLM_INNER = 1, CLM_DONE = 2 };
+
+template <int N>
+struct CoopLmSmem {
+    static constexpr int NDV = 7 * N + N * N + 12;   // doubles per system
+    static constexpr int NIV = 2 * N + 10;           // ints per system
+    static constexpr size_t BYTES = 32 * ((size_t)NDV * sizeof(double) + (size_t)NIV * sizeof(int));
+};
+
+// per-lane views into [element][32] shared arrays
+struct LaneVec {
+    double* p;
+    NLB_DEV double& operator[](int i) const { return p[i * 32]; }
+};
+template <int N>
+struct LaneMat {
+    double* p;
+    NLB_DEV double& operator()(int i, int j) const { return p[(i + j * N) * 32]; }
+};
+struct LaneIVec {
+    int* p;
+    NLB_DEV int& operator[](int i) const { return p[i * 32]; }
+};
+
+template <int N>
+NLB_DEV double clm_norm2(const LaneVec& v) {
+    Norm2 acc;
+    for (int i = 0; i < N; ++i) acc.add(v[i]);
+    return acc.value();
+}
+
+// lmsolve on the n x n block held in shared memory (strict lower triangle = scratch for S^T).
+template <int N>
+NLB_DEV void clm_qrsolve(const LaneMat<N>& r, const LaneIVec& ipvt, const LaneVec& diag, const LaneVec& qtb,
+                         const LaneVec& x, const LaneVec& sdiag, const LaneVec& wa) {
+    for (int j = 0; j < N; ++j) {
+        for (int i = j; i < N; ++i) r(i, j) = r(j, i);
+        x[j] = r(j, j);
+        wa[j] = qtb[j];
+    }
+    for (int j = 0; j < N; ++j) {
+        const double dl = diag[ipvt[j]];
+        if (dl != 0.0) {
+            for (int k = j; k < N; ++k) sdiag[k] = 0.0;
+            sdiag[j] = dl;
+            double qtbpj = 0.0;
+            for (int k = j; k < N; ++k) {
+                const double sk = sdiag[k];
+                if (sk == 0.0) continue;
+                double cs, sn;
+                const double rkk = r(k, k);
+                if (fabs(rkk) < fabs(sk)) {
+                    const double ctan = rkk / sk;
+                    sn = 0.5 / sqrt(0.25 + 0.25 * (ctan * ctan));
+                    cs = sn * ctan;
+                } else {
+                    const double tn = sk / rkk;
+                    cs = 0.5 / sqrt(0.25 + 0.25 * (tn * tn));
+                    sn = cs * tn;
+                }
+                r(k, k) = cs * rkk + sn * sk;
+                const double wk = wa[k];
+                double temp = cs * wk + sn * qtbpj;
+                qtbpj = -sn * wk + cs * qtbpj;
+                wa[k] = temp;
+                for (int i = k + 1; i < N; ++i) {
+                    const double rik = r(i, k), si = sdiag[i];
+                    temp = cs * rik + sn * si;
+                    sdiag[i] = -sn * rik + cs * si;
+                    r(i, k) = temp;
+                }
+            }
+        }
+        sdiag[j] = r(j, j);
+        r(j, j) = x[j];
+    }
+    int nsing = N;
+    for (int j = 0; j < N; ++j) {
+        if (sdiag[j] == 0.0 && nsing == N) nsing = j;
+        if (nsing < N) wa[j] = 0.0;
+    }
+    for (int j = nsing - 1; j >= 0; --j) {
+        double sm = 0.0;
+        for (int i = j + 1; i < nsing; ++i) sm += r(i, j) * wa[i];
+        wa[j] = (wa[j] - sm) / sdiag[j];
+    }
+    for (int j = 0; j < N; ++j) x[ipvt[j]] = wa[j];
+}
+
+// lmpar.  wa2 is the reference's m-element work array: its first n entries are w4h (shared
+// memory), entries n..m-1 are the tail of the HBM vector w4 (stride 32) — the in-loop dxnorm
+// runs over all m of them (src/nonlin_least_squares.f90:531).
+template <int N>
+NLB_DEV void clm_par(const LaneMat<N>& r, const LaneIVec& ipvt, const LaneVec& diag, const LaneVec& qtb, double delta,
+                     double& par, const LaneVec& x, const LaneVec& sdiag, const LaneVec& wa1, const LaneVec& w4h,
+                     const double* __restrict__ w4, int m) {
+    const double dwarf = 0x1p-1022;
+    int nsing = N;
+    for (int j = 0; j < N; ++j) {
+        wa1[j] = qtb[j];
+        if (r(j, j) == 0.0 && nsing == N) nsing = j;
+        if (nsing < N) wa1[j] = 0.0;
+    }
+    for (int j = nsing - 1; j >= 0; --j) {
+        wa1[j] = wa1[j] / r(j, j);
+        const double temp = wa1[j];
+        for (int i = 0; i < j; ++i) wa1[i] = wa1[i] - r(i, j) * temp;
+    }
+    for (int j = 0; j < N; ++j) x[ipvt[j]] = wa1[j];
+
+    int iter = 0;
+    for (int j = 0; j < N; ++j) w4h[j] = diag[j] * x[j];
+    double dxnorm = clm_norm2<N>(w4h);
+    double fp = dxnorm - delta;
+    if (fp <= 0.1 * delta) {
+        par = 0.0;
+        return;
+    }
+    double parl = 0.0;
+    if (nsing == N) {
+        for (int j = 0; j < N; ++j) {
+            const int l = ipvt[j];
+            wa1[j] = diag[l] * (w4h[l] / dxnorm);
+        }
+        for (int j = 0; j < N; ++j) {
+            double sm = 0.0;
+            for (int i = 0; i < j; ++i) sm += r(i, j) * wa1[i];
+            wa1[j] = (wa1[j] - sm) / r(j, j);
+        }
+        const double temp = clm_norm2<N>(wa1);
+        parl = ((fp / delta) / temp) / temp;
+    }
+    for (int j = 0; j < N; ++j) {
+        double sm = 0.0;
+        for (int i = 0; i <= j; ++i) sm += r(i, j) * qtb[i];
+        wa1[j] = sm / diag[ipvt[j]];
+    }
+    const double gnorm = clm_norm2<N>(wa1);
+    double paru = gnorm / delta;
+    if (paru == 0.0) paru = dwarf / nl_min(delta, 0.1);
+    par = nl_max(par, parl);
+    par = nl_min(par, paru);
+    if (par == 0.0) par = gnorm / dxnorm;
+
+    for (;;) {
+        ++iter;
+        if (par == 0.0) par = nl_max(dwarf, 1.0e-3 * paru);
+        double temp = sqrt(par);
+        for (int j = 0; j < N; ++j) wa1[j] = temp * diag[j];
+        clm_qrsolve<N>(r, ipvt, wa1, qtb, x, sdiag, w4h);
+        for (int j = 0; j < N; ++j) w4h[j] = diag[j] * x[j];
+        {
+            Norm2 acc;
+            for (int i = 0; i < N; ++i) acc.add(w4h[i]);
+            for (int i = N; i < m; ++i) acc.add(w4[(long long)i * 32]);
+            dxnorm = acc.value();
+        }
+        temp = fp;
+        fp = dxnorm - delta;
+        if (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
+        for (int j = 0; j < N; ++j) {
+            const int l = ipvt[j];
+            wa1[j] = diag[l] * (w4h[l] / dxnorm);
+        }
+        for (int j = 0; j < N; ++j) {
+            wa1[j] = wa1[j] / sdiag[j];
+            temp = wa1[j];
+            if (j + 1 < N)
+                for (int i = 0; i < N; ++i) wa1[i] = wa1[i] - r(i, j) * temp;
+        }
+        temp = clm_norm2<N>(wa1);
+        const double parc = ((fp / delta) / temp) / temp;
+        if (fp > 0.0) parl = nl_max(parl, par);
+        if (fp < 0.0) paru = nl_min(paru, par);
+        par = nl_max(parl, par + parc);
+    }
+}
+
+// scalar slots of a system in shared memory
+enum { SC_FNORM = 0, SC_PAR, SC_XNORM, SC_DELTA, SC_GNORM, SC_AJNORM, SC_AJJ, SC_PNORM, SC_TEMP, SC_H, SC_NSC = 12 };
+enum { SI_STATE = 0, SI_ITER, SI_NEVAL, SI_NJAC, SI_FLAG, SI_FCN, SI_XCN, SI_GCN, SI_PIVOT, SI_ACCEPT, SI_NSI = 10 };
+
+template <class F, int N>
+__global__ void __launch_bounds__(32 * N)
+coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, double* __restrict__ xg,
+               double* __restrict__ fg, const double* __restrict__ sys, const double* __restrict__ shared,
+               nlb_iteration_behavior* __restrict__ ibg, int32_t* __restrict__ statusg, double* __restrict__ ws) {
+    static_assert(F::N == N, "residual / kernel size mismatch");
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
+    const long long loc = (long long)blockIdx.x * 32 + lane;
+    const bool valid = loc < nsys;
+    const long long b = b0 + (valid ? loc : 0);
+
+    // shared memory carve-up: [element][lane]
+    double* sd = smem + lane;
+    const LaneVec x{sd}, diag{sd + 32 * N}, qtf{sd + 64 * N}, wa1{sd + 96 * N}, wa2{sd + 128 * N}, wa3{sd + 160 * N},
+        w4h{sd + 192 * N}, sc{sd + 32 * (7 * N + N * N)};
+    const LaneMat<N> R{sd + 224 * N};
+    int* si_base = reinterpret_cast<int*>(smem + 32 * CoopLmSmem<N>::NDV) + lane;
+    const LaneIVec ipvt{si_base}, pos{si_base + 32 * N}, si{si_base + 64 * N};
+
+    // HBM workspace of this group
+    const long long gstride = (long long)(N + 2) * m * 32;
+    double* J = ws + (long long)blockIdx.x * gstride + lane;        // J(i, c) = J[(i*N + c)*32]
+    double* fv = J + (long long)m * N * 32;                         // fvec(i) = fv[i*32]
+    double* w4 = fv + (long long)m * 32;                            // wa4(i)  = w4[i*32]
+    const double* ysys = sys + b;                                   // y(i)    = ysys[i*B]
+
+    const double eps = 0x1p-52;
+    const double ftol = p.fcn_tol, xtol = p.var_tol, gtol = p.grad_tol, fac = p.lm_factor;
+
+    // ---- phase 0: load x, fvec = F(x), fnorm --------------------------------------------
+    if (k == 0) {
+        si[SI_STATE] = valid ? CLM_NEED_JAC : CLM_DONE;
+        si[SI_ITER] = 1; si[SI_NEVAL] = 1; si[SI_NJAC] = 0; si[SI_FLAG] = 0;
+        si[SI_FCN] = 0; si[SI_XCN] = 0; si[SI_GCN] = 0; si[SI_ACCEPT] = 0;
+        sc[SC_PAR] = 0.0; sc[SC_XNORM] = 0.0; sc[SC_DELTA] = 0.0; sc[SC_GNORM] = 0.0;
+    }
+    x[k] = valid ? xg[(long long)k * B + b] : 0.0;
+    __syncthreads();
+    if (valid) {
+        double xl[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) xl[j] = x[j];
+        for (int i = k; i < m; i += N) fv[(long long)i * 32] = F::residual(xl, __ldg(shared + i), ysys[(long long)i * B]);
+    }
+    __syncthreads();
+    if (k == 0 && valid) {
+        Norm2 acc;
+        for (int i = 0; i < m; ++i) acc.add(fv[(long long)i * 32]);
+        sc[SC_FNORM] = acc.value();
+    }
+    __syncthreads();
+
+    for (;;) {
+        const int state0 = si[SI_STATE];
+        if (__syncthreads_and(state0 == CLM_DONE)) break;
+        const bool needjac = state0 == CLM_NEED_JAC;
+
+        // ---- phase J: forward-difference column k, its norm (vfh_jac_fcn :262-275, lmfactor :611-616)
+        if (needjac) {
+            double xl[N];
+            const double temp = x[k];
+            double h = 0x1p-26 * fabs(temp);
+            if (h == 0.0) h = 0x1p-26;
+#pragma unroll
+            for (int j = 0; j < N; ++j) xl[j] = (j == k) ? (temp + h) : x[j];
+            Norm2 acc;
+            for (int i = 0; i < m; ++i) {
+                const double f1 = F::residual(xl, __ldg(shared + i), ysys[(long long)i * B]);
+                const double v = (f1 - fv[(long long)i * 32]) / h;
+                J[((long long)i * N + k) * 32] = v;
+                acc.add(v);
+            }
+            const double cn = acc.value();
+            wa2[k] = cn;      // acnorm (physical column)
+            wa1[k] = cn;      // rdiag  (logical position)
+            wa3[k] = cn;      // wa
+            ipvt[k] = k;
+            pos[k] = k;
+            if (k == 0) si[SI_NJAC] = si[SI_NJAC] + 1;
+        }
+        __syncthreads();
+
+        // ---- phase QR: pivoted Householder, one logical column per step (lmfactor :619-666)
+        for (int j = 0; j < N; ++j) {
+            if (needjac && k == 0) {
+                int kmax = j;
+                double rmax = wa1[j];
+                for (int c = j + 1; c < N; ++c) {
+                    const double rc = wa1[c];
+                    if (rc > rmax) { rmax = rc; kmax = c; }
+                }
+                if (kmax != j) {
+                    wa1[kmax] = wa1[j];
+                    wa3[kmax] = wa3[j];
+                    const int pj = ipvt[j], pk = ipvt[kmax];
+                    ipvt[j] = pk; ipvt[kmax] = pj;
+                    pos[pk] = j; pos[pj] = kmax;
+                }
+                si[SI_PIVOT] = ipvt[j];
+            }
+            __syncthreads();
+            if (needjac && k == si[SI_PIVOT]) {
+                Norm2 acc;
+                for (int i = j; i < m; ++i) acc.add(J[((long long)i * N + k) * 32]);
+                double ajnorm = acc.value();
+                if (ajnorm != 0.0) {
+                    if (J[((long long)j * N + k) * 32] < 0.0) ajnorm = -ajnorm;
+                    for (int i = j; i < m; ++i) J[((long long)i * N + k) * 32] = J[((long long)i * N + k) * 32] / ajnorm;
+                    const double ajj = J[((long long)j * N + k) * 32] + 1.0;
+                    J[((long long)j * N + k) * 32] = ajj;
+                    sc[SC_AJJ] = ajj;
+                }
+                sc[SC_AJNORM] = ajnorm;
+            }
+            __syncthreads();
+            if (needjac) {
+                const int pc = si[SI_PIVOT];
+                const double ajnorm = sc[SC_AJNORM];
+                const int mypos = pos[k];
+                if (mypos > j && ajnorm != 0.0) {
+                    double sm = 0.0;
+#pragma unroll 4
+                    for (int i = j; i < m; ++i) sm += J[((long long)i * N + pc) * 32] * J[((long long)i * N + k) * 32];
+                    double temp = sm / sc[SC_AJJ];
+#pragma unroll 4
+                    for (int i = j; i < m; ++i)
+                        J[((long long)i * N + k) * 32] = J[((long long)i * N + k) * 32] - temp * J[((long long)i * N + pc) * 32];
+                    double rd = wa1[mypos];
+                    if (rd != 0.0) {
+                        temp = J[((long long)j * N + k) * 32] / rd;
+                        rd = rd * sqrt(nl_max(0.0, 1.0 - temp * temp));
+                        wa1[mypos] = rd;
+                        const double q = rd / wa3[mypos];
+                        if (!(0.05 * (q * q) > eps)) {
+                            Norm2 acc;
+                            for (int i = j + 1; i < m; ++i) acc.add(J[((long long)i * N + k) * 32]);
+                            rd = acc.value();
+                            wa1[mypos] = rd;
+                            wa3[mypos] = rd;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (needjac && k == 0) wa1[j] = -sc[SC_AJNORM];
+        }
+        __syncthreads();
+
+        // ---- phase QTF: wa4 = fvec; qtf = first n of Q^T fvec; R = top block (lss_solve :241-253)
+        if (needjac)
+            for (int i = k; i < m; i += N) w4[(long long)i * 32] = fv[(long long)i * 32];
+        __syncthreads();
+        for (int j = 0; j < N; ++j) {
+            if (needjac && k == 0) {
+                const int pc = ipvt[j];
+                const double ajj = J[((long long)j * N + pc) * 32];
+                double temp = 0.0;
+                if (ajj != 0.0) {
+                    double sm = 0.0;
+#pragma unroll 4
+                    for (int i = j; i < m; ++i) sm += J[((long long)i * N + pc) * 32] * w4[(long long)i * 32];
+                    temp = -sm / ajj;
+                }
+                sc[SC_TEMP] = temp;
+                sc[SC_AJJ] = ajj;
+            }
+            __syncthreads();
+            if (needjac && sc[SC_AJJ] != 0.0) {
+                const int pc = ipvt[j];
+                const double temp = sc[SC_TEMP];
+                for (int i = j + k; i < m; i += N) w4[(long long)i * 32] = w4[(long long)i * 32] + J[((long long)i * N + pc) * 32] * temp;
+            }
+            __syncthreads();
+            if (needjac && k == 0) qtf[j] = w4[(long long)j * 32];
+        }
+        if (needjac) {
+            // logical column k of R: strict upper part from J, diagonal = rdiag(k)
+            const int pc = ipvt[k];
+            for (int i = 0; i < k; ++i) R(i, k) = J[((long long)i * N + pc) * 32];
+            R(k, k) = wa1[k];
+        }
+        __syncthreads();
+
+        // ---- phases G + P on warp 0: scaling, gradient test, LM parameter, trial point --------
+        if (k == 0 && state0 != CLM_DONE) {
+            int state = state0;
+            const int iter = si[SI_ITER];
+            const double fnorm = sc[SC_FNORM];
+            if (state == CLM_NEED_JAC) {
+                if (iter == 1) {
+                    for (int j = 0; j < N; ++j) {
+                        const double a = wa2[j];
+                        diag[j] = (a == 0.0) ? 1.0 : a;
+                    }
+                    for (int j = 0; j < N; ++j) wa3[j] = diag[j] * x[j];
+                    const double xnorm = clm_norm2<N>(wa3);
+                    double delta = fac * xnorm;
+                    if (delta == 0.0) delta = fac;
+                    sc[SC_XNORM] = xnorm;
+                    sc[SC_DELTA] = delta;
+                }
+                double gnorm = 0.0;
+                if (fnorm != 0.0) {
+                    for (int j = 0; j < N; ++j) {
+                        const double acn = wa2[ipvt[j]];
+                        if (acn == 0.0) continue;
+                        double sm = 0.0;
+                        for (int i = 0; i <= j; ++i) sm += R(i, j) * (qtf[i] / fnorm);
+                        gnorm = nl_max(gnorm, fabs(sm / acn));
+                    }
+                }
+                sc[SC_GNORM] = gnorm;
+                if (gnorm <= gtol) {
+                    si[SI_GCN] = 1;
+                    state = CLM_DONE;
+                } else {
+                    for (int j = 0; j < N; ++j) diag[j] = nl_max(diag[j], wa2[j]);
+                    state = CLM_INNER;
+                }
+            }
+            if (state == CLM_INNER) {
+                double par = sc[SC_PAR];
+                double delta = sc[SC_DELTA];
+                clm_par<N>(R, ipvt, diag, qtf, delta, par, wa1, wa2, wa3, w4h, w4, m);
+                for (int j = 0; j < N; ++j) {
+                    const double pj = -wa1[j];
+                    wa1[j] = pj;
+                    wa2[j] = x[j] + pj;
+                    wa3[j] = diag[j] * pj;
+                }
+                const double pnorm = clm_norm2<N>(wa3);
+                if (iter == 1) delta = nl_min(delta, pnorm);
+                sc[SC_PAR] = par;
+                sc[SC_DELTA] = delta;
+                sc[SC_PNORM] = pnorm;
+            }
+            si[SI_STATE] = state;
+        }
+        __syncthreads();
+
+        // ---- phase E: wa4 = F(x + p), rows split over the n threads of the system -------------
+        const bool inner = si[SI_STATE] == CLM_INNER;
+        if (inner) {
+            double xl[N];
+#pragma unroll
+            for (int j = 0; j < N; ++j) xl[j] = wa2[j];
+            for (int i = k; i < m; i += N) w4[(long long)i * 32] = F::residual(xl, __ldg(shared + i), ysys[(long long)i * B]);
+        }
+        __syncthreads();
+
+        // ---- phase A on warp 0: gain ratio, step bound, acceptance, convergence (lss_solve :297-365)
+        if (k == 0 && inner) {
+            int iter = si[SI_ITER];
+            const int neval = si[SI_NEVAL] + 1;
+            si[SI_NEVAL] = neval;
+            double fnorm = sc[SC_FNORM], par = sc[SC_PAR], delta = sc[SC_DELTA], xnorm = sc[SC_XNORM];
+            const double pnorm = sc[SC_PNORM], gnorm = sc[SC_GNORM];
+            double fnorm1;
+            {
+                Norm2 acc;
+                for (int i = 0; i < m; ++i) acc.add(w4[(long long)i * 32]);
+                fnorm1 = acc.value();
+            }
+            double actred = -1.0;
+            if (0.1 * fnorm1 < fnorm) { const double q = fnorm1 / fnorm; actred = 1.0 - q * q; }
+            double temp = 0.0;
+            for (int j = 0; j < N; ++j) {
+                wa3[j] = 0.0;
+                temp = wa1[ipvt[j]];
+                for (int i = 0; i <= j; ++i) wa3[i] = wa3[i] + R(i, j) * temp;
+            }
+            const double temp1 = clm_norm2<N>(wa3) / fnorm;
+            const double temp2 = (sqrt(par) * pnorm) / fnorm;
+            const double prered = temp1 * temp1 + temp2 * temp2 / 0.5;
+            const double dirder = -(temp1 * temp1 + temp2 * temp2);
+            double ratio = 0.0;
+            if (prered != 0.0) ratio = actred / prered;
+            if (ratio <= 0.25) {
+                if (actred >= 0.0) temp = 0.5;
+                if (actred < 0.0) temp = 0.5 * dirder / (dirder + 0.5 * actred);
+                if (0.1 * fnorm1 >= fnorm || temp < 0.1) temp = 0.1;
+                delta = temp * nl_min(delta, pnorm / 0.1);
+                par = par / temp;
+            } else if (!(par != 0.0 && ratio < 0.75)) {
+                delta = pnorm / 0.5;
+                par = 0.5 * par;
+            }
+            const bool accept = ratio >= 1.0e-4;
+            if (accept) {
+                for (int j = 0; j < N; ++j) {
+                    const double xn = wa2[j];
+                    x[j] = xn;
+                    wa2[j] = diag[j] * xn;
+                }
+                xnorm = clm_norm2<N>(wa2);
+                fnorm = fnorm1;
+                ++iter;
+            }
+            si[SI_ACCEPT] = accept;
+            bool fcnvrg = false, xcnvrg = false;
+            if (fabs(actred) <= ftol && prered <= ftol && 0.5 * ratio <= 1.0) fcnvrg = true;
+            if (delta <= xtol * xnorm) xcnvrg = true;
+            int flag = 0;
+            int state = CLM_INNER;
+            if (fcnvrg || xcnvrg) {
+                state = CLM_DONE;
+            } else {
+                if (neval >= p.max_fcn_evals) flag = NLB_CONVERGENCE_ERROR;
+                if (fabs(actred) <= eps && prered <= eps && 0.5 * ratio <= 1.0) flag = NLB_TOLERANCE_TOO_SMALL_ERROR;
+                if (delta <= eps * xnorm) flag = NLB_TOLERANCE_TOO_SMALL_ERROR;
+                if (gnorm <= eps) flag = NLB_TOLERANCE_TOO_SMALL_ERROR;
+                if (flag != 0) state = CLM_DONE;
+                else if (accept) state = CLM_NEED_JAC;
+            }
+            si[SI_FCN] = fcnvrg; si[SI_XCN] = xcnvrg; si[SI_FLAG] = flag;
+            si[SI_ITER] = iter; si[SI_STATE] = state;
+            sc[SC_FNORM] = fnorm; sc[SC_PAR] = par; sc[SC_DELTA] = delta; sc[SC_XNORM] = xnorm;
+        }
+        __syncthreads();
+        // ---- phase C: accepted step -> fvec = wa4 ---------------------------------------------
+        if (inner && si[SI_ACCEPT]) {
+            for (int i = k; i < m; i += N) fv[(long long)i * 32] = w4[(long long)i * 32];
+        }
+        __syncthreads();
+        if (k == 0) si[SI_ACCEPT] = 0;
+    }
+
+    // ---- results ---------------------------------------------------------------------------
+    if (valid) {
+        xg[(long long)k * B + b] = x[k];
+        for (int i = k; i < m; i += N) fg[(long long)i * B + b] = fv[(long long)i * 32];
+        if (k == 0) {
+            if (ibg) {
+                nlb_iteration_behavior o;
+                o.iter_count = si[SI_ITER]; o.fcn_count = si[SI_NEVAL]; o.jacobian_count = si[SI_NJAC]; o.gradient_count = 0;
+                o.converge_on_fcn = si[SI_FCN]; o.converge_on_chng = si[SI_XCN]; o.converge_on_zero_diff = si[SI_GCN];
+                ibg[b] = o;
+            }
+            if (statusg) statusg[b] = si[SI_FLAG] != 0 ? NLB_CONVERGENCE_ERROR : NLB_NO_ERROR;
+        }
+    }
+}
+
+int launch_coop_lm(int fcn_id, const DevParams& p, long long B, int m, int n, double* x, double* fvec, const double* sys,
+                   const double* shared, nlb_iteration_behavior* ib, int32_t* status, cudaStream_t s, int64_t* launches);
+
+}  // namespace nlb

@@ -344,3 +344,98 @@ def test_cxx_host_mirror(engine, tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     assert "Solution: (5.00000, 3.00000)" in r.stdout
     assert "Iterations: 11" in r.stdout and "Function Evaluations: 15" in r.stdout and "Jacobian Evaluations: 1" in r.stdout
+
+
+# ---------------------------------------------------------------------------------------------
+# CTA-per-system kernels (run-time sized families)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,B", [(8, 300), (16, 200), (32, 100), (64, 96)])
+def test_c5_broyden_rosenbrock_parity(engine, oracle, n, B):
+    """BASELINE config 5 (extended Rosenbrock, quasi-Newton + line search): the CTA-per-system kernel
+    keeps the reference's summation order, so it is bit-identical to the oracle."""
+    import nonlin_b200 as nb
+    from nonlin_b200 import workloads as W
+
+    w = W.c5_broyden_rosenbrock(B, n=n)
+    x, f, ib, st = run_engine(nb, w)
+    xo, fo, ibo, sto = oracle.solve_batch(w["solver"], w["fcn"], w["x0"], m=n)
+    assert (sto == 0).all()
+    assert_parity(x, f, ib, st, xo, fo, ibo, sto)
+    onf = ib["converge_on_fcn"] == 1               # the root of the extended Rosenbrock system is x = 1
+    assert onf.mean() > 0.9 and np.abs(x[:, onf] - 1.0).max() < 1e-6
+    # without the line search and with another Jacobian interval
+    s = nb.quasi_newton_solver(); s.set_use_line_search(False); s.set_jacobian_interval(3); s.set_max_fcn_evals(500)
+    x, f, ib, st = run_engine(nb, w, solver=s)
+    xo, fo, ibo, sto = oracle.solve_batch(w["solver"], w["fcn"], w["x0"], m=n,
+                                          params=oracle.params(use_line_search=0, jacobian_interval=3, max_fcn_evals=500))
+    assert np.array_equal(st, sto) and np.array_equal(x, xo) and np.array_equal(f, fo) and np.array_equal(ib, ibo)
+
+
+def test_c5_golden(engine):
+    import nonlin_b200 as nb
+    from nonlin_b200 import workloads as W
+
+    g = np.load(os.path.join(HERE, "golden", "oracle_batches.npz"))
+    B = g["C5_status"].shape[0]
+    x, f, ib, st = run_engine(nb, W.c5_broyden_rosenbrock(B))
+    assert np.array_equal(x, g["C5_x"]) and np.array_equal(f, g["C5_f"])
+    assert np.array_equal(ib.view(np.int32).reshape(B, 7), g["C5_ib"]) and np.array_equal(st, g["C5_status"])
+
+
+def test_runtime_family_eval(engine, oracle):
+    import nonlin_b200 as nb
+    from nonlin_b200 import workloads as W
+
+    for w in (W.c4_lm_rational(64, m=128), W.lm_expdecay4(64, m=48), W.c5_broyden_rosenbrock(64, n=16)):
+        obj = nb.vecfcn_helper(); obj.set_fcn(w["fcn"], w["m"], w["n"])
+        if w["shared"] is not None:
+            obj.set_shared_data(w["shared"])
+        f = obj.fcn(w["x0"], args=w["args"])
+        for b in (0, 17, 63):
+            fo = oracle.eval_fcn(w["fcn"], w["x0"][:, b], m=w["m"], sys=None if w["args"] is None else w["args"][:, b], shared=w["shared"])
+            assert np.array_equal(f[:, b], fo)
+
+
+@pytest.mark.parametrize("name,B,kw", [("LM4", 200, {"m": 64}), ("LM4", 70, {"m": 33}), ("C4", 40, {"m": 64}), ("C4", 33, {"m": 256})])
+def test_tall_lm_parity(engine, oracle, name, B, kw):
+    """Curve-fit LM with run-time m (BASELINE config 4 family and the 4-parameter fits): thread per
+    (system, column), Jacobian in HBM, every m-length sum walked in the reference's order -> bitwise."""
+    import nonlin_b200 as nb
+    from nonlin_b200 import workloads as W
+
+    w = W.WORKLOADS[name](B, **kw)
+    x, f, ib, st = run_engine(nb, w)
+    xo, fo, ibo, sto = oracle.solve_batch(w["solver"], w["fcn"], w["x0"], m=w["m"], sys=w["args"], shared=w["shared"],
+                                          params=oracle_params(oracle, w))
+    assert (sto == 0).mean() > 0.9
+    assert_parity(x, f, ib, st, xo, fo, ibo, sto)
+
+
+@pytest.mark.parametrize("name,kw", [("LM4", {}), ("C4", {"m": 256})])
+def test_tall_lm_golden(engine, name, kw):
+    import nonlin_b200 as nb
+    from nonlin_b200 import workloads as W
+
+    g = np.load(os.path.join(HERE, "golden", "oracle_batches.npz"))
+    B = g[name + "_status"].shape[0]
+    x, f, ib, st = run_engine(nb, W.WORKLOADS[name](B, **kw))
+    assert np.array_equal(x, g[name + "_x"]) and np.array_equal(f, g[name + "_f"])
+    assert np.array_equal(ib.view(np.int32).reshape(B, 7), g[name + "_ib"]) and np.array_equal(st, g[name + "_status"])
+
+
+def test_c4_full_m_sample(engine, oracle):
+    """m = 4096, n = 16 at a batch the oracle finishes in seconds; default max_fcn_evals makes a part of
+    the systems fail, which must agree too."""
+    import nonlin_b200 as nb
+    from nonlin_b200 import workloads as W
+
+    w = W.c4_lm_rational(48, m=4096)
+    x, f, ib, st = run_engine(nb, w)
+    xo, fo, ibo, sto = oracle.solve_batch(w["solver"], w["fcn"], w["x0"], m=4096, sys=w["args"], shared=w["shared"],
+                                          params=oracle_params(oracle, w))
+    assert_parity(x, f, ib, st, xo, fo, ibo, sto)
+    w["settings"] = {"set_max_fcn_evals": 12}
+    x, f, ib, st = run_engine(nb, w)
+    xo, fo, ibo, sto = oracle.solve_batch(w["solver"], w["fcn"], w["x0"], m=4096, sys=w["args"], shared=w["shared"],
+                                          params=oracle.params(max_fcn_evals=12))
+    assert (sto != 0).any() and np.array_equal(st, sto) and np.array_equal(x, xo) and np.array_equal(ib, ibo)

@@ -54,7 +54,7 @@ def parse():
 
 
 def default_batch(name):
-    return {"C4": 4096, "C5": 16384}.get(name, BATCH_PER_GPU)
+    return {"C4": 2368, "C5": 16384, "LM4": BATCH_PER_GPU}.get(name, BATCH_PER_GPU)
 
 
 def workload_label(w, B):
@@ -210,8 +210,8 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # engine arm
 # ---------------------------------------------------------------------------------------------
-def make_solver(nb, w):
-    s = {"least_squares": nb.least_squares_solver, "newton": nb.newton_solver, "quasi_newton": nb.quasi_newton_solver}[w["solver"]]()
+def make_solver(nb, w, eng):
+    s = {"least_squares": nb.least_squares_solver, "newton": nb.newton_solver, "quasi_newton": nb.quasi_newton_solver}[w["solver"]](engine=eng)
     for k, v in w["settings"].items():
         getattr(s, k)(v)
     return s
@@ -227,7 +227,7 @@ class DeviceRun:
         self.obj = nb.vecfcn_helper(); self.obj.set_fcn(w["fcn"], w["m"], w["n"])
         if w["shared"] is not None:
             self.obj.set_shared_data(torch.from_numpy(w["shared"]).to(dev))
-        self.solver = make_solver(nb, w)
+        self.solver = make_solver(nb, w, eng)
         self.x0 = torch.from_numpy(w["x0"]).to(dev)
         self.args = None if w["args"] is None else torch.from_numpy(w["args"]).to(dev)
         # the solve is in place: one fresh copy of x0 per step, made before the timed region
@@ -293,7 +293,7 @@ def e2e_run(nb, torch, w, eng, steps, warmup):
     obj = nb.vecfcn_helper(); obj.set_fcn(w["fcn"], w["m"], w["n"])
     if w["shared"] is not None:
         obj.set_shared_data(w["shared"])
-    solver = make_solver(nb, w)
+    solver = make_solver(nb, w, eng)
     pin = lambda a: torch.from_numpy(a).pin_memory()
     x0 = pin(w["x0"]); args = None if w["args"] is None else pin(w["args"])
     x = torch.empty_like(x0).pin_memory()

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnonlin_b200.so")
+LIB_PATH = os.environ.get("NLB_LIB") or os.path.join(HERE, "libnonlin_b200.so")   # NLB_LIB: tuning builds only
 
 # API-level errors (include/nonlin_batch.h)
 NLB_OK = 0

@@ -132,9 +132,16 @@ def _stream_of(*arrays):
 
 
 def _device_of(*arrays):
+    """Device of the first CUDA tensor among the arguments; for host-only calls, torch's current
+    device when torch is already in use (one process per GPU under torchrun), else device 0."""
     for a in arrays:
         if a is not None and _is_torch(a) and a.is_cuda:
             return a.device.index or 0
+    import sys
+
+    torch = sys.modules.get("torch")
+    if torch is not None and torch.cuda.is_available() and torch.cuda.is_initialized():
+        return torch.cuda.current_device()
     return None
 
 

@@ -61,6 +61,21 @@ NLB_DEV double clm_norm2(const LaneVec& v) {
     return acc.value();
 }
 
+
+// Norm2 of v[i0*stride], ..., v[(i1-1)*stride] in index order; loads are issued eight at a time so that
+// their latency overlaps (the accumulation itself stays strictly sequential).
+NLB_DEV void clm_norm2_strided(Norm2& acc, const double* __restrict__ v, long long stride, int i0, int i1) {
+    int i = i0;
+    for (; i + 8 <= i1; i += 8) {
+        double t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = v[(long long)(i + u) * stride];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc.add(t[u]);
+    }
+    for (; i < i1; ++i) acc.add(v[(long long)i * stride]);
+}
+
 // lmsolve on the n x n block held in shared memory (strict lower triangle = scratch for S^T).
 template <int N>
 NLB_DEV void clm_qrsolve(const LaneMat<N>& r, const LaneIVec& ipvt, const LaneVec& diag, const LaneVec& qtb,
@@ -184,7 +199,7 @@ NLB_DEV void clm_par(const LaneMat<N>& r, const LaneIVec& ipvt, const LaneVec& d
         {
             Norm2 acc;
             for (int i = 0; i < N; ++i) acc.add(w4h[i]);
-            for (int i = N; i < m; ++i) acc.add(w4[(long long)i * 32]);
+            clm_norm2_strided(acc, w4, 32, N, m);
             dxnorm = acc.value();
         }
         temp = fp;
@@ -260,7 +275,7 @@ coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, do
     __syncthreads();
     if (k == 0 && valid) {
         Norm2 acc;
-        for (int i = 0; i < m; ++i) acc.add(fv[(long long)i * 32]);
+        clm_norm2_strided(acc, fv, 32, 0, m);
         sc[SC_FNORM] = acc.value();
     }
     __syncthreads();
@@ -316,10 +331,11 @@ coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, do
             __syncthreads();
             if (needjac && k == si[SI_PIVOT]) {
                 Norm2 acc;
-                for (int i = j; i < m; ++i) acc.add(J[((long long)i * N + k) * 32]);
+                clm_norm2_strided(acc, J + k * 32, (long long)N * 32, j, m);
                 double ajnorm = acc.value();
                 if (ajnorm != 0.0) {
                     if (J[((long long)j * N + k) * 32] < 0.0) ajnorm = -ajnorm;
+#pragma unroll 8
                     for (int i = j; i < m; ++i) J[((long long)i * N + k) * 32] = J[((long long)i * N + k) * 32] / ajnorm;
                     const double ajj = J[((long long)j * N + k) * 32] + 1.0;
                     J[((long long)j * N + k) * 32] = ajj;
@@ -333,13 +349,15 @@ coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, do
                 const double ajnorm = sc[SC_AJNORM];
                 const int mypos = pos[k];
                 if (mypos > j && ajnorm != 0.0) {
+                    const double* __restrict__ cp = J + pc * 32;     // pivot column (read only here)
+                    double* __restrict__ ck = J + k * 32;            // own column, pc != k
+                    const long long rs = (long long)N * 32;
                     double sm = 0.0;
-#pragma unroll 4
-                    for (int i = j; i < m; ++i) sm += J[((long long)i * N + pc) * 32] * J[((long long)i * N + k) * 32];
+#pragma unroll 8
+                    for (int i = j; i < m; ++i) sm += cp[i * rs] * ck[i * rs];
                     double temp = sm / sc[SC_AJJ];
-#pragma unroll 4
-                    for (int i = j; i < m; ++i)
-                        J[((long long)i * N + k) * 32] = J[((long long)i * N + k) * 32] - temp * J[((long long)i * N + pc) * 32];
+#pragma unroll 8
+                    for (int i = j; i < m; ++i) ck[i * rs] = ck[i * rs] - temp * cp[i * rs];
                     double rd = wa1[mypos];
                     if (rd != 0.0) {
                         temp = J[((long long)j * N + k) * 32] / rd;
@@ -348,7 +366,7 @@ coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, do
                         const double q = rd / wa3[mypos];
                         if (!(0.05 * (q * q) > eps)) {
                             Norm2 acc;
-                            for (int i = j + 1; i < m; ++i) acc.add(J[((long long)i * N + k) * 32]);
+                            clm_norm2_strided(acc, J + k * 32, (long long)N * 32, j + 1, m);
                             rd = acc.value();
                             wa1[mypos] = rd;
                             wa3[mypos] = rd;
@@ -372,7 +390,7 @@ coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, do
                 double temp = 0.0;
                 if (ajj != 0.0) {
                     double sm = 0.0;
-#pragma unroll 4
+#pragma unroll 8
                     for (int i = j; i < m; ++i) sm += J[((long long)i * N + pc) * 32] * w4[(long long)i * 32];
                     temp = -sm / ajj;
                 }
@@ -473,7 +491,7 @@ coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, do
             double fnorm1;
             {
                 Norm2 acc;
-                for (int i = 0; i < m; ++i) acc.add(w4[(long long)i * 32]);
+                clm_norm2_strided(acc, w4, 32, 0, m);
                 fnorm1 = acc.value();
             }
             double actred = -1.0;

@@ -111,10 +111,24 @@ DevParams to_dev(const nlb_params* p) {
 // ---------------------------------------------------------------------------------------
 // thread-per-system kernels
 // ---------------------------------------------------------------------------------------
-constexpr int TPS_BLOCK = 128;
+#ifndef NLB_TPS_BLOCK
+#define NLB_TPS_BLOCK 128
+#endif
+constexpr int TPS_BLOCK = NLB_TPS_BLOCK;
+// Minimum resident CTAs per SM asked of ptxas.  Measured on B200 (scripts/sweep_variants.py): capping the
+// 2x2 Broyden kernel at 80 registers (6 CTAs/SM) is 11 % faster than 110 registers (4 CTAs/SM); the LM and
+// Newton kernels do not gain from tighter caps.
+template <int SOLVER>
+constexpr int tps_min_blocks() {
+#ifdef NLB_TPS_MINB
+    return NLB_TPS_MINB;
+#else
+    return SOLVER == 2 ? 6 : 1;
+#endif
+}
 
 template <class F, int SOLVER>
-__global__ void __launch_bounds__(TPS_BLOCK)
+__global__ void __launch_bounds__(TPS_BLOCK, tps_min_blocks<SOLVER>())
 tps_solve_kernel(DevParams p, long long B, double* __restrict__ x, double* __restrict__ fvec,
                  const double* __restrict__ sys, const double* __restrict__ shared,
                  nlb_iteration_behavior* __restrict__ ib, int32_t* __restrict__ status) {

@@ -294,11 +294,29 @@ coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, do
 #pragma unroll
             for (int j = 0; j < N; ++j) xl[j] = (j == k) ? (temp + h) : x[j];
             Norm2 acc;
-            for (int i = 0; i < m; ++i) {
-                const double f1 = F::residual(xl, __ldg(shared + i), ysys[(long long)i * B]);
-                const double v = (f1 - fv[(long long)i * 32]) / h;
-                J[((long long)i * N + k) * 32] = v;
-                acc.add(v);
+            {
+                int i = 0;
+                for (; i + 4 <= m; i += 4) {
+                    double tt[4], yy[4], ff[4], v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        tt[u] = __ldg(shared + i + u);
+                        yy[u] = ysys[(long long)(i + u) * B];
+                        ff[u] = fv[(long long)(i + u) * 32];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) v[u] = (F::residual(xl, tt[u], yy[u]) - ff[u]) / h;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) J[((long long)(i + u) * N + k) * 32] = v[u];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) acc.add(v[u]);
+                }
+                for (; i < m; ++i) {
+                    const double f1 = F::residual(xl, __ldg(shared + i), ysys[(long long)i * B]);
+                    const double v = (f1 - fv[(long long)i * 32]) / h;
+                    J[((long long)i * N + k) * 32] = v;
+                    acc.add(v);
+                }
             }
             const double cn = acc.value();
             wa2[k] = cn;      // acnorm (physical column)
@@ -335,8 +353,19 @@ coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, do
                 double ajnorm = acc.value();
                 if (ajnorm != 0.0) {
                     if (J[((long long)j * N + k) * 32] < 0.0) ajnorm = -ajnorm;
-#pragma unroll 8
-                    for (int i = j; i < m; ++i) J[((long long)i * N + k) * 32] = J[((long long)i * N + k) * 32] / ajnorm;
+                    {   // a(j:m, k) /= ajnorm, eight independent loads in flight
+                        double* col = J + k * 32;
+                        const long long rs = (long long)N * 32;
+                        int i = j;
+                        for (; i + 8 <= m; i += 8) {
+                            double t[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) t[u] = col[(i + u) * rs];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) col[(i + u) * rs] = t[u] / ajnorm;
+                        }
+                        for (; i < m; ++i) col[i * rs] = col[i * rs] / ajnorm;
+                    }
                     const double ajj = J[((long long)j * N + k) * 32] + 1.0;
                     J[((long long)j * N + k) * 32] = ajj;
                     sc[SC_AJJ] = ajj;
@@ -353,11 +382,29 @@ coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, do
                     double* __restrict__ ck = J + k * 32;            // own column, pc != k
                     const long long rs = (long long)N * 32;
                     double sm = 0.0;
-#pragma unroll 8
-                    for (int i = j; i < m; ++i) sm += cp[i * rs] * ck[i * rs];
+                    {
+                        int i = j;
+                        for (; i + 8 <= m; i += 8) {
+                            double a[8], c[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) { a[u] = cp[(i + u) * rs]; c[u] = ck[(i + u) * rs]; }
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) sm += a[u] * c[u];
+                        }
+                        for (; i < m; ++i) sm += cp[i * rs] * ck[i * rs];
+                    }
                     double temp = sm / sc[SC_AJJ];
-#pragma unroll 8
-                    for (int i = j; i < m; ++i) ck[i * rs] = ck[i * rs] - temp * cp[i * rs];
+                    {
+                        int i = j;
+                        for (; i + 8 <= m; i += 8) {
+                            double a[8], c[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) { a[u] = cp[(i + u) * rs]; c[u] = ck[(i + u) * rs]; }
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) ck[(i + u) * rs] = c[u] - temp * a[u];
+                        }
+                        for (; i < m; ++i) ck[i * rs] = ck[i * rs] - temp * cp[i * rs];
+                    }
                     double rd = wa1[mypos];
                     if (rd != 0.0) {
                         temp = J[((long long)j * N + k) * 32] / rd;
@@ -381,7 +428,17 @@ coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, do
 
         // ---- phase QTF: wa4 = fvec; qtf = first n of Q^T fvec; R = top block (lss_solve :241-253)
         if (needjac)
-            for (int i = k; i < m; i += N) w4[(long long)i * 32] = fv[(long long)i * 32];
+        {
+            int i = k;
+            for (; i + 3 * N < m; i += 4 * N) {
+                double t[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) t[u] = fv[(long long)(i + u * N) * 32];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) w4[(long long)(i + u * N) * 32] = t[u];
+            }
+            for (; i < m; i += N) w4[(long long)i * 32] = fv[(long long)i * 32];
+        }
         __syncthreads();
         for (int j = 0; j < N; ++j) {
             if (needjac && k == 0) {
@@ -390,8 +447,19 @@ coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, do
                 double temp = 0.0;
                 if (ajj != 0.0) {
                     double sm = 0.0;
-#pragma unroll 8
-                    for (int i = j; i < m; ++i) sm += J[((long long)i * N + pc) * 32] * w4[(long long)i * 32];
+                    {
+                        const double* col = J + pc * 32;
+                        const long long rs = (long long)N * 32;
+                        int i = j;
+                        for (; i + 8 <= m; i += 8) {
+                            double a[8], c[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) { a[u] = col[(i + u) * rs]; c[u] = w4[(long long)(i + u) * 32]; }
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) sm += a[u] * c[u];
+                        }
+                        for (; i < m; ++i) sm += col[i * rs] * w4[(long long)i * 32];
+                    }
                     temp = -sm / ajj;
                 }
                 sc[SC_TEMP] = temp;
@@ -401,7 +469,17 @@ coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, do
             if (needjac && sc[SC_AJJ] != 0.0) {
                 const int pc = ipvt[j];
                 const double temp = sc[SC_TEMP];
-                for (int i = j + k; i < m; i += N) w4[(long long)i * 32] = w4[(long long)i * 32] + J[((long long)i * N + pc) * 32] * temp;
+                const double* col = J + pc * 32;
+                const long long rs = (long long)N * 32;
+                int i = j + k;
+                for (; i + 3 * N < m; i += 4 * N) {
+                    double a[4], c[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { a[u] = col[(i + u * N) * rs]; c[u] = w4[(long long)(i + u * N) * 32]; }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) w4[(long long)(i + u * N) * 32] = c[u] + a[u] * temp;
+                }
+                for (; i < m; i += N) w4[(long long)i * 32] = w4[(long long)i * 32] + col[i * rs] * temp;
             }
             __syncthreads();
             if (needjac && k == 0) qtf[j] = w4[(long long)j * 32];
@@ -477,7 +555,15 @@ coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, do
             double xl[N];
 #pragma unroll
             for (int j = 0; j < N; ++j) xl[j] = wa2[j];
-            for (int i = k; i < m; i += N) w4[(long long)i * 32] = F::residual(xl, __ldg(shared + i), ysys[(long long)i * B]);
+            int i = k;
+            for (; i + 3 * N < m; i += 4 * N) {
+                double tt[4], yy[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { tt[u] = __ldg(shared + i + u * N); yy[u] = ysys[(long long)(i + u * N) * B]; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) w4[(long long)(i + u * N) * 32] = F::residual(xl, tt[u], yy[u]);
+            }
+            for (; i < m; i += N) w4[(long long)i * 32] = F::residual(xl, __ldg(shared + i), ysys[(long long)i * B]);
         }
         __syncthreads();
 
@@ -552,7 +638,15 @@ coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, do
         __syncthreads();
         // ---- phase C: accepted step -> fvec = wa4 ---------------------------------------------
         if (inner && si[SI_ACCEPT]) {
-            for (int i = k; i < m; i += N) fv[(long long)i * 32] = w4[(long long)i * 32];
+            int i = k;
+            for (; i + 3 * N < m; i += 4 * N) {
+                double t[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) t[u] = w4[(long long)(i + u * N) * 32];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) fv[(long long)(i + u * N) * 32] = t[u];
+            }
+            for (; i < m; i += N) fv[(long long)i * 32] = w4[(long long)i * 32];
         }
         __syncthreads();
         if (k == 0) si[SI_ACCEPT] = 0;

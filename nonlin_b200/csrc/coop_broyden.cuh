@@ -246,7 +246,7 @@ struct ExtRosenbrockCoop {
 
 template <class F, int N>
 __global__ void __launch_bounds__(N)
-coop_broyden_kernel(DevParams p, long long B, double* __restrict__ xg, double* __restrict__ fg,
+coop_broyden_kernel(DevParams p, long long nsys, long long B, double* __restrict__ xg, double* __restrict__ fg,
                     const double* __restrict__ sys, const double* __restrict__ shared,
                     nlb_iteration_behavior* __restrict__ ibg, int32_t* __restrict__ statusg) {
     using S = CoopBroydenSmem<N>;
@@ -269,7 +269,7 @@ coop_broyden_kernel(DevParams p, long long B, double* __restrict__ xg, double* _
     double* xp = tau + N;     // perturbed copy of x for the forward differences
     const int tid = threadIdx.x;
     const long long b = blockIdx.x;
-    if (b >= B) return;
+    if (b >= nsys) return;
     SysCtx c{sys ? sys + b : nullptr, shared, B, N, N};
 
     const double ftol = p.fcn_tol, xtol = p.var_tol, gtol = p.grad_tol;

@@ -11,7 +11,7 @@ namespace {
 enum { SOLVER_LM = 0, SOLVER_NEWTON = 1, SOLVER_BROYDEN = 2 };
 
 template <class F, int N>
-int launch_broyden(const DevParams& p, long long B, double* x, double* fvec, const double* sys, const double* shared,
+int launch_broyden(const DevParams& p, long long nsys, long long B, double* x, double* fvec, const double* sys, const double* shared,
                    nlb_iteration_behavior* ib, int32_t* status, cudaStream_t s, int64_t* launches) {
     using S = CoopBroydenSmem<N>;
     static bool configured = false;
@@ -21,7 +21,7 @@ int launch_broyden(const DevParams& p, long long B, double* x, double* fvec, con
             return NLB_ERR_CUDA;
         configured = true;
     }
-    coop_broyden_kernel<F, N><<<(unsigned)B, N, S::BYTES, s>>>(p, B, x, fvec, sys, shared, ib, status);
+    coop_broyden_kernel<F, N><<<(unsigned)nsys, N, S::BYTES, s>>>(p, nsys, B, x, fvec, sys, shared, ib, status);
     ++*launches;
     return cudaGetLastError() == cudaSuccess ? NLB_OK : NLB_ERR_CUDA;
 }
@@ -49,7 +49,7 @@ __global__ void rosenbrock_eval_kernel(long long B, int n, const double* __restr
 }
 
 template <class F, int N>
-int launch_lm(const DevParams& p, long long B, int m, double* x, double* fvec, const double* sys, const double* shared,
+int launch_lm(const DevParams& p, long long ntot, long long B, int m, double* x, double* fvec, const double* sys, const double* shared,
               nlb_iteration_behavior* ib, int32_t* status, cudaStream_t s, int64_t* launches) {
     using S = CoopLmSmem<N>;
     static bool configured = false;
@@ -63,11 +63,11 @@ int launch_lm(const DevParams& p, long long B, int m, double* x, double* fvec, c
     const size_t per_sys = (size_t)(N + 2) * (size_t)m * sizeof(double);
     long long chunk = (long long)((8ull << 30) / per_sys) / 32 * 32;
     if (chunk < 32) chunk = 32;
-    if (chunk > B) chunk = (B + 31) / 32 * 32;
+    if (chunk > ntot) chunk = (ntot + 31) / 32 * 32;
     double* ws = nullptr;
     if (cudaMallocAsync((void**)&ws, per_sys * (size_t)chunk, s) != cudaSuccess) return NLB_ERR_CUDA;
-    for (long long b0 = 0; b0 < B; b0 += chunk) {
-        const long long nsys = (B - b0 < chunk) ? (B - b0) : chunk;
+    for (long long b0 = 0; b0 < ntot; b0 += chunk) {
+        const long long nsys = (ntot - b0 < chunk) ? (ntot - b0) : chunk;
         const unsigned grid = (unsigned)((nsys + 31) / 32);
         coop_lm_kernel<F, N><<<grid, 32 * N, S::BYTES, s>>>(p, B, b0, nsys, m, x, fvec, sys, shared, ib, status, ws);
         ++*launches;
@@ -79,30 +79,31 @@ int launch_lm(const DevParams& p, long long B, int m, double* x, double* fvec, c
 
 }  // namespace
 
-int launch_coop_lm(int fcn_id, const DevParams& p, long long B, int m, int n, double* x, double* fvec, const double* sys,
+int launch_coop_lm(int fcn_id, const DevParams& p, long long nsys, long long B, int m, int n, double* x, double* fvec, const double* sys,
                    const double* shared, nlb_iteration_behavior* ib, int32_t* status, cudaStream_t s, int64_t* launches) {
     if (m < n) return NLB_ERR_UNSUPPORTED;
     switch (fcn_id) {
-        case FCN_RATIONAL_7_8: return launch_lm<Rational78, 16>(p, B, m, x, fvec, sys, shared, ib, status, s, launches);
-        case FCN_EXP_SUM_8: return launch_lm<ExpSum8, 16>(p, B, m, x, fvec, sys, shared, ib, status, s, launches);
-        case FCN_EXP_DECAY_4: return launch_lm<ExpDecay4, 4>(p, B, m, x, fvec, sys, shared, ib, status, s, launches);
+        case FCN_RATIONAL_7_8: return launch_lm<Rational78, 16>(p, nsys, B, m, x, fvec, sys, shared, ib, status, s, launches);
+        case FCN_EXP_SUM_8: return launch_lm<ExpSum8, 16>(p, nsys, B, m, x, fvec, sys, shared, ib, status, s, launches);
+        case FCN_EXP_DECAY_4: return launch_lm<ExpDecay4, 4>(p, nsys, B, m, x, fvec, sys, shared, ib, status, s, launches);
         default: return NLB_ERR_UNSUPPORTED;
     }
 }
 
-int launch_coop_solve(int solver, int fcn_id, const DevParams& p, long long B, int m, int n, double* x, double* fvec,
+int launch_coop_solve(int solver, int fcn_id, const DevParams& p, long long nsys, long long B, int m, int n, double* x,
+                      double* fvec,
                       const double* sys, const double* shared, nlb_iteration_behavior* ib, int32_t* status,
                       cudaStream_t s, int64_t* launches) {
     if (solver == SOLVER_BROYDEN && fcn_id == FCN_EXT_ROSENBROCK) {
         switch (n) {
-            case 8: return launch_broyden<ExtRosenbrockCoop, 8>(p, B, x, fvec, sys, shared, ib, status, s, launches);
-            case 16: return launch_broyden<ExtRosenbrockCoop, 16>(p, B, x, fvec, sys, shared, ib, status, s, launches);
-            case 32: return launch_broyden<ExtRosenbrockCoop, 32>(p, B, x, fvec, sys, shared, ib, status, s, launches);
-            case 64: return launch_broyden<ExtRosenbrockCoop, 64>(p, B, x, fvec, sys, shared, ib, status, s, launches);
+            case 8: return launch_broyden<ExtRosenbrockCoop, 8>(p, nsys, B, x, fvec, sys, shared, ib, status, s, launches);
+            case 16: return launch_broyden<ExtRosenbrockCoop, 16>(p, nsys, B, x, fvec, sys, shared, ib, status, s, launches);
+            case 32: return launch_broyden<ExtRosenbrockCoop, 32>(p, nsys, B, x, fvec, sys, shared, ib, status, s, launches);
+            case 64: return launch_broyden<ExtRosenbrockCoop, 64>(p, nsys, B, x, fvec, sys, shared, ib, status, s, launches);
             default: return NLB_ERR_UNSUPPORTED;
         }
     }
-    if (solver == SOLVER_LM) return launch_coop_lm(fcn_id, p, B, m, n, x, fvec, sys, shared, ib, status, s, launches);
+    if (solver == SOLVER_LM) return launch_coop_lm(fcn_id, p, nsys, B, m, n, x, fvec, sys, shared, ib, status, s, launches);
     return NLB_ERR_UNSUPPORTED;
 }
 

@@ -6,7 +6,8 @@
 namespace nlb {
 
 // Returns NLB_OK, NLB_ERR_UNSUPPORTED (no kernel for this combination) or NLB_ERR_CUDA.
-int launch_coop_solve(int solver, int fcn_id, const DevParams& p, long long B, int m, int n, double* x, double* fvec,
+int launch_coop_solve(int solver, int fcn_id, const DevParams& p, long long nsys, long long B, int m, int n, double* x,
+                      double* fvec,
                       const double* sys, const double* shared, nlb_iteration_behavior* ib, int32_t* status,
                       cudaStream_t s, int64_t* launches);
 

@@ -668,7 +668,7 @@ coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, do
     }
 }
 
-int launch_coop_lm(int fcn_id, const DevParams& p, long long B, int m, int n, double* x, double* fvec, const double* sys,
+int launch_coop_lm(int fcn_id, const DevParams& p, long long nsys, long long B, int m, int n, double* x, double* fvec, const double* sys,
                    const double* shared, nlb_iteration_behavior* ib, int32_t* status, cudaStream_t s, int64_t* launches);
 
 }  // namespace nlb

@@ -28,6 +28,8 @@ struct nlb_handle {
     void* dbuf[NSLOT] = {nullptr};
     size_t dcap[NSLOT] = {0};
     int64_t* dstats = nullptr;
+    cudaStream_t pipe[2] = {nullptr, nullptr};   // copy/compute pipeline for host-resident batches
+    cudaEvent_t ev_in = nullptr, ev_out[2] = {nullptr, nullptr};
     std::mutex mu;
 };
 
@@ -129,12 +131,13 @@ constexpr int tps_min_blocks() {
 
 template <class F, int SOLVER>
 __global__ void __launch_bounds__(TPS_BLOCK, tps_min_blocks<SOLVER>())
-tps_solve_kernel(DevParams p, long long B, double* __restrict__ x, double* __restrict__ fvec,
+tps_solve_kernel(DevParams p, long long nsys, long long B, double* __restrict__ x, double* __restrict__ fvec,
                  const double* __restrict__ sys, const double* __restrict__ shared,
                  nlb_iteration_behavior* __restrict__ ib, int32_t* __restrict__ status) {
+    // nsys systems starting at the (pre-offset) pointers; B is the SoA stride of the whole batch
     constexpr int M = F::M, N = F::N;
     const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (b >= B) return;
+    if (b >= nsys) return;
     double xl[N], fl[M];
 #pragma unroll
     for (int j = 0; j < N; ++j) xl[j] = x[j * B + b];
@@ -255,11 +258,12 @@ __global__ void fp64_peak_kernel(double* out, int iters, double seed) {
 // dispatch
 // ---------------------------------------------------------------------------------------
 template <class F, int SOLVER>
-int launch_tps_solve(nlb_handle* h, const DevParams& p, long long B, double* x, double* fvec, const double* sys,
-                     const double* shared, nlb_iteration_behavior* ib, int32_t* status, cudaStream_t s) {
-    if (B == 0) return NLB_OK;
-    const unsigned grid = (unsigned)((B + TPS_BLOCK - 1) / TPS_BLOCK);
-    tps_solve_kernel<F, SOLVER><<<grid, TPS_BLOCK, 0, s>>>(p, B, x, fvec, sys, shared, ib, status);
+int launch_tps_solve(nlb_handle* h, const DevParams& p, long long nsys, long long B, double* x, double* fvec,
+                     const double* sys, const double* shared, nlb_iteration_behavior* ib, int32_t* status,
+                     cudaStream_t s) {
+    if (nsys == 0) return NLB_OK;
+    const unsigned grid = (unsigned)((nsys + TPS_BLOCK - 1) / TPS_BLOCK);
+    tps_solve_kernel<F, SOLVER><<<grid, TPS_BLOCK, 0, s>>>(p, nsys, B, x, fvec, sys, shared, ib, status);
     ++h->launches;
     NLB_CUDA(h, cudaGetLastError());
     return NLB_OK;
@@ -270,17 +274,17 @@ int launch_tps_solve(nlb_handle* h, const DevParams& p, long long B, double* x, 
 #define NLB_FIXED_FCNS(X) NLB_SQUARE_FCNS(X) X(LsqPolyFit)
 
 template <int SOLVER>
-int dispatch_tps(nlb_handle* h, int fcn_id, const DevParams& p, long long B, double* x, double* fvec,
+int dispatch_tps(nlb_handle* h, int fcn_id, const DevParams& p, long long nsys, long long B, double* x, double* fvec,
                  const double* sys, const double* shared, nlb_iteration_behavior* ib, int32_t* status,
                  cudaStream_t s) {
     switch (fcn_id) {
 #define X(F) \
-    case F::ID: return launch_tps_solve<F, SOLVER>(h, p, B, x, fvec, sys, shared, ib, status, s);
+    case F::ID: return launch_tps_solve<F, SOLVER>(h, p, nsys, B, x, fvec, sys, shared, ib, status, s);
         NLB_SQUARE_FCNS(X)
 #undef X
         case LsqPolyFit::ID:
             if constexpr (SOLVER == SOLVER_LM)
-                return launch_tps_solve<LsqPolyFit, SOLVER_LM>(h, p, B, x, fvec, sys, shared, ib, status, s);
+                return launch_tps_solve<LsqPolyFit, SOLVER_LM>(h, p, nsys, B, x, fvec, sys, shared, ib, status, s);
             else
                 return set_err(h, NLB_ERR_SIZE, "Newton / quasi-Newton need m == n");
         default: return set_err(h, NLB_ERR_UNSUPPORTED, "no thread-per-system kernel for this residual");
@@ -327,45 +331,81 @@ int solve_batch(nlb_handle* h, int solver, const nlb_params* params, int fcn_id,
     if (B == 0) return NLB_OK;
     cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
 
-    Staged ax, af, as, ash, aib, ast;
-    if ((rc = stage_in(h, 0, x, sizeof(double) * (size_t)n * B, true, s, &ax))) return rc;
-    if ((rc = stage_in(h, 1, fvec, sizeof(double) * (size_t)m * B, false, s, &af))) return rc;
-    if ((rc = stage_in(h, 2, sys, sizeof(double) * (size_t)sys_len * B, true, s, &as))) return rc;
+    // Arguments are SoA arrays of `rows` x B elements; host-resident ones get a device twin.
+    struct Arg { Staged st; size_t rows, elem; bool in, out; };
+    Arg a[5] = {
+        {{}, (size_t)n, sizeof(double), true, true},                       // x
+        {{}, (size_t)m, sizeof(double), false, true},                      // fvec
+        {{}, (size_t)sys_len, sizeof(double), true, false},                // per-system data
+        {{}, 1, sizeof(nlb_iteration_behavior), false, true},              // ib
+        {{}, 1, sizeof(int32_t), false, true},                             // status
+    };
+    const void* user[5] = {x, fvec, sys, ib, status};
+    const int slot[5] = {0, 1, 2, 4, 5};
+    bool any_staged = false;
+    for (int i = 0; i < 5; ++i) {
+        if ((rc = stage_in(h, slot[i], user[i], a[i].rows * a[i].elem * (size_t)B, false, s, &a[i].st))) return rc;
+        any_staged = any_staged || a[i].st.staged;
+    }
+    Staged ash;
     if ((rc = stage_in(h, 3, shared, sizeof(double) * (size_t)shared_len, true, s, &ash))) return rc;
-    if ((rc = stage_in(h, 4, ib, sizeof(nlb_iteration_behavior) * (size_t)B, false, s, &aib))) return rc;
-    if ((rc = stage_in(h, 5, status, sizeof(int32_t) * (size_t)B, false, s, &ast))) return rc;
+    any_staged = any_staged || ash.staged;
 
     const DevParams p = to_dev(params);
     const FcnInfo& fi = fcn_table()[fcn_id];
-    if (fi.m != 0 && fi.n != 0) {
-        switch (solver) {
-            case SOLVER_LM:
-                rc = dispatch_tps<SOLVER_LM>(h, fcn_id, p, B, (double*)ax.dev, (double*)af.dev, (const double*)as.dev,
-                                             (const double*)ash.dev, (nlb_iteration_behavior*)aib.dev, (int32_t*)ast.dev, s);
-                break;
-            case SOLVER_NEWTON:
-                rc = dispatch_tps<SOLVER_NEWTON>(h, fcn_id, p, B, (double*)ax.dev, (double*)af.dev, (const double*)as.dev,
-                                                 (const double*)ash.dev, (nlb_iteration_behavior*)aib.dev, (int32_t*)ast.dev, s);
-                break;
-            default:
-                rc = dispatch_tps<SOLVER_BROYDEN>(h, fcn_id, p, B, (double*)ax.dev, (double*)af.dev, (const double*)as.dev,
-                                                  (const double*)ash.dev, (nlb_iteration_behavior*)aib.dev, (int32_t*)ast.dev, s);
+    auto launch = [&](long long b0, long long cnt, cudaStream_t st) -> int {
+        double* dx = (double*)a[0].st.dev + b0;
+        double* df = (double*)a[1].st.dev + b0;
+        const double* ds = a[2].st.dev ? (const double*)a[2].st.dev + b0 : nullptr;
+        nlb_iteration_behavior* dib = a[3].st.dev ? (nlb_iteration_behavior*)a[3].st.dev + b0 : nullptr;
+        int32_t* dst = a[4].st.dev ? (int32_t*)a[4].st.dev + b0 : nullptr;
+        const double* dsh = (const double*)ash.dev;
+        int r;
+        if (fi.m != 0 && fi.n != 0) {
+            switch (solver) {
+                case SOLVER_LM: r = dispatch_tps<SOLVER_LM>(h, fcn_id, p, cnt, B, dx, df, ds, dsh, dib, dst, st); break;
+                case SOLVER_NEWTON: r = dispatch_tps<SOLVER_NEWTON>(h, fcn_id, p, cnt, B, dx, df, ds, dsh, dib, dst, st); break;
+                default: r = dispatch_tps<SOLVER_BROYDEN>(h, fcn_id, p, cnt, B, dx, df, ds, dsh, dib, dst, st);
+            }
+        } else {
+            r = launch_coop_solve(solver, fcn_id, p, cnt, B, m, n, dx, df, ds, dsh, dib, dst, st, &h->launches);
+            if (r == NLB_ERR_UNSUPPORTED) return set_err(h, r, "no cooperative kernel for this (solver, residual, size)");
+            if (r == NLB_ERR_CUDA) return set_err(h, r, "cooperative kernel launch", cudaGetLastError());
         }
-    } else {
-        rc = launch_coop_solve(solver, fcn_id, p, B, m, n, (double*)ax.dev, (double*)af.dev, (const double*)as.dev,
-                               (const double*)ash.dev, (nlb_iteration_behavior*)aib.dev, (int32_t*)ast.dev, s,
-                               &h->launches);
-        if (rc == NLB_ERR_UNSUPPORTED) return set_err(h, rc, "no cooperative kernel for this (solver, residual, size)");
-        if (rc == NLB_ERR_CUDA) return set_err(h, rc, "cooperative kernel launch", cudaGetLastError());
-    }
-    if (rc) return rc;
+        return r;
+    };
 
-    const bool any_staged = ax.staged || af.staged || aib.staged || ast.staged || as.staged || ash.staged;
-    if ((rc = stage_out(h, ax, s))) return rc;
-    if ((rc = stage_out(h, af, s))) return rc;
-    if ((rc = stage_out(h, aib, s))) return rc;
-    if ((rc = stage_out(h, ast, s))) return rc;
-    if (any_staged) NLB_CUDA(h, cudaStreamSynchronize(s));
+    if (!any_staged) return launch(0, B, s);          // all-device call: one asynchronous launch on the caller's stream
+
+    // Host-resident batch: split it into chunks and pipeline H2D copy / kernel / D2H copy on two
+    // streams, so that the two copy engines and the SMs overlap (the path is PCIe-bound).
+    const int nchunk = B >= (1 << 18) ? 8 : (B >= (1 << 15) ? 2 : 1);
+    const long long chunk = (B + nchunk - 1) / nchunk;
+    NLB_CUDA(h, cudaEventRecord(h->ev_in, s));
+    for (int q = 0; q < 2; ++q) NLB_CUDA(h, cudaStreamWaitEvent(h->pipe[q], h->ev_in, 0));
+    int c = 0;
+    for (long long b0 = 0; b0 < B; b0 += chunk, ++c) {
+        const long long cnt = (B - b0 < chunk) ? (B - b0) : chunk;
+        cudaStream_t st = h->pipe[c & 1];
+        for (int i = 0; i < 5; ++i) {
+            if (a[i].st.staged && a[i].in)
+                NLB_CUDA(h, cudaMemcpy2DAsync((char*)a[i].st.dev + b0 * a[i].elem, (size_t)B * a[i].elem,
+                                              (const char*)a[i].st.user + b0 * a[i].elem, (size_t)B * a[i].elem,
+                                              (size_t)cnt * a[i].elem, a[i].rows, cudaMemcpyHostToDevice, st));
+        }
+        if ((rc = launch(b0, cnt, st))) return rc;
+        for (int i = 0; i < 5; ++i) {
+            if (a[i].st.staged && a[i].out)
+                NLB_CUDA(h, cudaMemcpy2DAsync((char*)a[i].st.user + b0 * a[i].elem, (size_t)B * a[i].elem,
+                                              (const char*)a[i].st.dev + b0 * a[i].elem, (size_t)B * a[i].elem,
+                                              (size_t)cnt * a[i].elem, a[i].rows, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    for (int q = 0; q < 2; ++q) {
+        NLB_CUDA(h, cudaEventRecord(h->ev_out[q], h->pipe[q]));
+        NLB_CUDA(h, cudaStreamWaitEvent(s, h->ev_out[q], 0));
+    }
+    NLB_CUDA(h, cudaStreamSynchronize(s));
     return NLB_OK;
 }
 
@@ -389,6 +429,11 @@ int nlb_create(nlb_handle** handle, int device) {
     nlb_handle* h = new nlb_handle();
     h->device = device;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->pipe[0], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->pipe[1], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_out[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_out[1], cudaEventDisableTiming) != cudaSuccess ||
         cudaMalloc(&h->dstats, sizeof(int64_t) * NLB_STAT_COUNT) != cudaSuccess) {
         delete h;
         return NLB_ERR_CUDA;
@@ -404,6 +449,11 @@ int nlb_destroy(nlb_handle* h) {
         if (h->dbuf[i]) cudaFree(h->dbuf[i]);
     if (h->dstats) cudaFree(h->dstats);
     if (h->stream) cudaStreamDestroy(h->stream);
+    for (int q = 0; q < 2; ++q) {
+        if (h->pipe[q]) cudaStreamDestroy(h->pipe[q]);
+        if (h->ev_out[q]) cudaEventDestroy(h->ev_out[q]);
+    }
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
     delete h;
     return NLB_OK;
 }

@@ -28,6 +28,9 @@ struct nlb_handle {
     void* dbuf[NSLOT] = {nullptr};
     size_t dcap[NSLOT] = {0};
     int64_t* dstats = nullptr;
+    unsigned long long* dcursor = nullptr;         // work-queue cursors of the persistent kernels (16 slots)
+    unsigned cursor_next = 0;
+    int num_sms = 0;
     cudaStream_t pipe[2] = {nullptr, nullptr};   // copy/compute pipeline for host-resident batches
     cudaEvent_t ev_in = nullptr, ev_out[2] = {nullptr, nullptr};
     std::mutex mu;
@@ -164,6 +167,15 @@ tps_solve_kernel(DevParams p, long long nsys, long long B, double* __restrict__ 
     if (status) status[b] = st.status;
 }
 
+// Persistent variant for Newton: grid = resident CTAs only, lanes pull systems from a cursor.
+template <class F>
+__global__ void __launch_bounds__(TPS_BLOCK)
+tps_newton_refill_kernel(DevParams p, long long nsys, long long B, unsigned long long* cursor, double* __restrict__ x,
+                         double* __restrict__ fvec, const double* __restrict__ sys, const double* __restrict__ shared,
+                         nlb_iteration_behavior* __restrict__ ib, int32_t* __restrict__ status) {
+    tps_newton_refill<F>(p, nsys, B, cursor, x, fvec, sys, shared, ib, status);
+}
+
 template <class F>
 __global__ void __launch_bounds__(TPS_BLOCK)
 tps_eval_kernel(long long B, const double* __restrict__ x, double* __restrict__ fvec,
@@ -269,6 +281,27 @@ int launch_tps_solve(nlb_handle* h, const DevParams& p, long long nsys, long lon
     return NLB_OK;
 }
 
+template <class F>
+int launch_tps_newton_refill(nlb_handle* h, const DevParams& p, long long nsys, long long B, double* x, double* fvec,
+                             const double* sys, const double* shared, nlb_iteration_behavior* ib, int32_t* status,
+                             cudaStream_t s) {
+    if (nsys == 0) return NLB_OK;
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+        NLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, tps_newton_refill_kernel<F>, TPS_BLOCK, 0));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
+    long long grid = (nsys + TPS_BLOCK - 1) / TPS_BLOCK;
+    const long long resident = (long long)h->num_sms * ctas_per_sm;
+    if (grid > resident) grid = resident;
+    unsigned long long* cursor = h->dcursor + (h->cursor_next++ & 15u);
+    NLB_CUDA(h, cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), s));
+    tps_newton_refill_kernel<F><<<(unsigned)grid, TPS_BLOCK, 0, s>>>(p, nsys, B, cursor, x, fvec, sys, shared, ib, status);
+    ++h->launches;
+    NLB_CUDA(h, cudaGetLastError());
+    return NLB_OK;
+}
+
 #define NLB_SQUARE_FCNS(X) \
     X(Misc2Fcn) X(Misc2FcnA) X(PoorlyScaled2Fcn) X(PowellBadlyScaled) X(Misc2Fcn01) X(Polar) X(PolarScaled)
 #define NLB_FIXED_FCNS(X) NLB_SQUARE_FCNS(X) X(LsqPolyFit)
@@ -278,8 +311,12 @@ int dispatch_tps(nlb_handle* h, int fcn_id, const DevParams& p, long long nsys, 
                  const double* sys, const double* shared, nlb_iteration_behavior* ib, int32_t* status,
                  cudaStream_t s) {
     switch (fcn_id) {
-#define X(F) \
-    case F::ID: return launch_tps_solve<F, SOLVER>(h, p, nsys, B, x, fvec, sys, shared, ib, status, s);
+#define X(F)                                                                                              \
+    case F::ID:                                                                                           \
+        if constexpr (SOLVER == SOLVER_NEWTON)                                                            \
+            return launch_tps_newton_refill<F>(h, p, nsys, B, x, fvec, sys, shared, ib, status, s);       \
+        else                                                                                              \
+            return launch_tps_solve<F, SOLVER>(h, p, nsys, B, x, fvec, sys, shared, ib, status, s);
         NLB_SQUARE_FCNS(X)
 #undef X
         case LsqPolyFit::ID:
@@ -434,7 +471,9 @@ int nlb_create(nlb_handle** handle, int device) {
         cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_out[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_out[1], cudaEventDisableTiming) != cudaSuccess ||
-        cudaMalloc(&h->dstats, sizeof(int64_t) * NLB_STAT_COUNT) != cudaSuccess) {
+        cudaMalloc(&h->dstats, sizeof(int64_t) * NLB_STAT_COUNT) != cudaSuccess ||
+        cudaMalloc(&h->dcursor, sizeof(unsigned long long) * 16) != cudaSuccess ||
+        cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
         delete h;
         return NLB_ERR_CUDA;
     }
@@ -448,6 +487,7 @@ int nlb_destroy(nlb_handle* h) {
     for (int i = 0; i < nlb_handle::NSLOT; ++i)
         if (h->dbuf[i]) cudaFree(h->dbuf[i]);
     if (h->dstats) cudaFree(h->dstats);
+    if (h->dcursor) cudaFree(h->dcursor);
     if (h->stream) cudaStreamDestroy(h->stream);
     for (int q = 0; q < 2; ++q) {
         if (h->pipe[q]) cudaStreamDestroy(h->pipe[q]);

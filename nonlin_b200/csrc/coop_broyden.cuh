@@ -57,8 +57,28 @@ template <int N>
 NLB_DEV void cb_reflect_trailing(double* a, int i, double tau, int tid) {
     constexpr int LD = N + 1;
     if (tau == 0.0) return;
-    int lastv = N - i;                                   // DLARF's scan for trailing zeros of v
-    while (lastv > 0 && a[(i + lastv - 1) + i * LD] == 0.0) --lastv;
+    // DLARF's scan for the last non-zero row of v, done in parallel: thread r tests v(r); the index of
+    // the highest set bit of the ballots is the same integer the sequential scan returns.
+    int lastv;
+    {
+        const bool nz = tid >= i && a[tid + i * LD] != 0.0;
+        if constexpr (N <= 32) {
+            const unsigned m = __ballot_sync(0xffffffffu >> (32 - N), nz);
+            lastv = m ? (32 - __clz(m)) - i : 0;
+        } else {
+            __shared__ unsigned ballots[N / 32];
+            const unsigned m = __ballot_sync(0xffffffffu, nz);
+            if ((tid & 31) == 0) ballots[tid >> 5] = m;
+            __syncthreads();
+            lastv = 0;
+#pragma unroll
+            for (int w = N / 32 - 1; w >= 0; --w) {
+                const unsigned mw = ballots[w];
+                if (lastv == 0 && mw) lastv = w * 32 + (32 - __clz(mw)) - i;
+            }
+            __syncthreads();
+        }
+    }
     if (lastv <= 0) return;
     if (tid > i) {
         const double* v = a + i + i * LD;
@@ -164,16 +184,24 @@ NLB_DEV void cb_qr_rank1_update(double* q, double* r, const double* u, const dou
     }
     __syncthreads();
     // DQRTV1: the Givens chain that folds w into w(1), bottom-up (strictly sequential)
+    // The chain only needs r of each rotation; it is evaluated (redundantly, uniformly) with the
+    // division-free part of DLARTG, the partial r's are kept in sn[], and thread i then computes
+    // c(i), s(i) of its own rotation from the same (f, g) pair — the same values, off the chain.
     double w0;
     {
         double rr = w[N - 1];
         for (int i = N - 2; i >= 0; --i) {
-            double c, s, t;
-            dlartg(w[i], rr, c, s, t);
-            if (tid == 0) { cs[i] = c; sn[i] = s; }
-            rr = t;
+            if (tid == 0) sn[i] = rr;                      // g of rotation i
+            rr = dlartg_r(w[i], rr);
         }
         w0 = rr;
+    }
+    __syncthreads();
+    if (tid < N - 1) {
+        double c, s2, t;
+        dlartg(w[tid], sn[tid], c, s2, t);
+        cs[tid] = c;
+        sn[tid] = s2;
     }
     __syncthreads();
     // DQRQH: R -> upper Hessenberg, thread t owns column t
@@ -395,9 +423,12 @@ coop_broyden_kernel(DevParams p, long long nsys, long long B, double* __restrict
                     ls_status = NLB_DIVERGENT_BEHAVIOR_ERROR;
                     f = 0.0;
                 } else {
+                    __syncthreads();
+                    w[tid] = fabs(df[tid]) / nl_max(fabs(xold[tid]), 1.0);
+                    __syncthreads();
                     double test = 0.0;
                     for (int i = 0; i < N; ++i) {
-                        const double tt = fabs(df[i]) / nl_max(fabs(xold[i]), 1.0);
+                        const double tt = w[i];
                         if (tt > test) test = tt;
                     }
                     const double alamin = 0x1p-51 / test;
@@ -446,11 +477,11 @@ coop_broyden_kernel(DevParams p, long long nsys, long long B, double* __restrict
             xcnvrg = false; fcnvrg = false; gcnvrg = false;
             if (cb_maxabs<N>(fvec) < ftol) { fcnvrg = true; check = true; }
             else {
+                __syncthreads();
+                w[tid] = fabs(x[tid] - xold[tid]) / nl_max(fabs(x[tid]), 1.0);
+                __syncthreads();
                 double xnorm = 0.0;
-                for (int i = 0; i < N; ++i) {
-                    const double tt = fabs(x[i] - xold[i]) / nl_max(fabs(x[i]), 1.0);
-                    xnorm = nl_max(tt, xnorm);
-                }
+                for (int i = 0; i < N; ++i) xnorm = nl_max(w[i], xnorm);
                 if (xnorm < xtol) { xcnvrg = true; check = true; }
             }
             (void)gtol;

@@ -157,6 +157,7 @@ struct Dnrm2 {
         const double ssml = 0x1p537;
         const double sbig = 0x1p-538;
         const double ax = fabs(x);
+        if (ax == 0.0) return;   // would add (0*ssml)^2 = +0 to asml: no effect on any accumulator
         if (ax > tbig) {
             const double t = ax * sbig;
             abig += t * t;
@@ -235,6 +236,21 @@ NLB_DEV void dlartg(double f, double g, double& c, double& s, double& r) {
         s = gs / r;
         r = r * u;
     }
+}
+
+// r of DLARTG alone (same branches, same operations, no c and s): for the sequential Givens chains.
+NLB_DEV double dlartg_r(double f, double g) {
+    const double safmin = 0x1p-1022;
+    const double safmax = 0x1p1022;
+    const double rtmin = 0x1p-511;
+    const double rtmax = 0x1.6a09e667f3bcdp+510;
+    const double f1 = fabs(f), g1 = fabs(g);
+    if (g == 0.0) return f;
+    if (f == 0.0) return g1;
+    if (f1 > rtmin && f1 < rtmax && g1 > rtmin && g1 < rtmax) return nl_sign(sqrt(f * f + g * g), f);
+    const double u = nl_min(safmax, nl_max(safmin, nl_max(f1, g1)));
+    const double fs = f / u, gs = g / u;
+    return nl_sign(sqrt(fs * fs + gs * gs), f) * u;
 }
 
 }  // namespace nlb

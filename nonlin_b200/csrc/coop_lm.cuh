@@ -348,29 +348,35 @@ coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, do
             }
             __syncthreads();
             if (needjac && k == si[SI_PIVOT]) {
+                // ajnorm = norm2(a(j:m, pivot)): strictly sequential, one thread
                 Norm2 acc;
                 clm_norm2_strided(acc, J + k * 32, (long long)N * 32, j, m);
                 double ajnorm = acc.value();
-                if (ajnorm != 0.0) {
-                    if (J[((long long)j * N + k) * 32] < 0.0) ajnorm = -ajnorm;
-                    {   // a(j:m, k) /= ajnorm, eight independent loads in flight
-                        double* col = J + k * 32;
-                        const long long rs = (long long)N * 32;
-                        int i = j;
-                        for (; i + 8 <= m; i += 8) {
-                            double t[8];
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) t[u] = col[(i + u) * rs];
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) col[(i + u) * rs] = t[u] / ajnorm;
-                        }
-                        for (; i < m; ++i) col[i * rs] = col[i * rs] / ajnorm;
-                    }
-                    const double ajj = J[((long long)j * N + k) * 32] + 1.0;
-                    J[((long long)j * N + k) * 32] = ajj;
-                    sc[SC_AJJ] = ajj;
-                }
+                if (ajnorm != 0.0 && J[((long long)j * N + k) * 32] < 0.0) ajnorm = -ajnorm;
                 sc[SC_AJNORM] = ajnorm;
+            }
+            __syncthreads();
+            if (needjac && sc[SC_AJNORM] != 0.0) {
+                // a(j:m, pivot) /= ajnorm is elementwise: rows are split over the n threads of the system
+                const double ajnorm = sc[SC_AJNORM];
+                double* col = J + si[SI_PIVOT] * 32;
+                const long long rs = (long long)N * 32;
+                int i = j + k;
+                for (; i + 3 * N < m; i += 4 * N) {
+                    double t[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) t[u] = col[(i + u * N) * rs];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) t[u] = t[u] / ajnorm;
+                    if (i == j) { t[0] = t[0] + 1.0; sc[SC_AJJ] = t[0]; }      // a(j,j) = a(j,j)/ajnorm + 1
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) col[(i + u * N) * rs] = t[u];
+                }
+                for (; i < m; i += N) {
+                    double t = col[i * rs] / ajnorm;
+                    if (i == j) { t = t + 1.0; sc[SC_AJJ] = t; }
+                    col[i * rs] = t;
+                }
             }
             __syncthreads();
             if (needjac) {

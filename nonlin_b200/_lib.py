@@ -77,7 +77,7 @@ assert IB_DTYPE.itemsize == 28
 def load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            "nonlin_b200: %s is missing. Build it with `python -m nonlin_b200.build` "
+            "nonlin_b200: %s is missing. Build it with `python nonlin_b200/build.py` "
             "(nvcc, sm_100a). The engine has no CPU fallback." % LIB_PATH
         )
     lib = C.CDLL(LIB_PATH)

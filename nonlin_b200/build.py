@@ -1,6 +1,6 @@
 """Build the engine's shared library in-tree with nvcc for sm_100a (no JIT cache, no arch list).
 
-    python -m nonlin_b200.build [--force] [--verbose]
+    python nonlin_b200/build.py [--force] [--verbose]
 
 The parity build passes -fmad=false: every multiply-add is a DMUL followed by a DADD, as in a
 default gfortran build of the reference.

@@ -128,7 +128,7 @@ constexpr int tps_min_blocks() {
 #ifdef NLB_TPS_MINB
     return NLB_TPS_MINB;
 #else
-    return SOLVER == 2 ? 6 : 1;
+    return SOLVER == 2 ? 6 : (SOLVER == 0 ? 3 : 1);
 #endif
 }
 

@@ -27,6 +27,7 @@ NLB_DEV double nl_sign(double a, double b) { return copysign(fabs(a), b); }
 // 235,291,299,313,346,475,501,511,531,554,612,642,660 and src/nonlin_linesearch.f90:569).
 struct Norm2 {
     double scale = 1.0, ssq = 0.0;
+#ifdef NLB_NORM2_BRANCHY
     NLB_DEV void add(double x) {
         if (x != 0.0) {
             double a = fabs(x);
@@ -40,15 +41,58 @@ struct Norm2 {
             }
         }
     }
+#else
+    NLB_DEV void add(double x) {
+        if (x != 0.0) {
+            // one division serves both cases (scale/a when a new maximum arrives, a/scale otherwise);
+            // the two updates are the ones libgfortran performs, selected after the fact
+            const double a = fabs(x);
+            const bool up = scale < a;
+            const double t = (up ? scale : a) / (up ? a : scale);
+            const double tt = t * t;
+            ssq = up ? (1.0 + ssq * t * t) : (ssq + tt);
+            scale = up ? a : scale;
+        }
+    }
+#endif
     NLB_DEV double value() const { return scale * sqrt(ssq); }
 };
 
+// NORM2 of a[i0*stride .. (i1-1)*stride] (per-thread array, run-time bounds): the loads are issued seven at
+// a time so their latency overlaps; the accumulation order is unchanged.
+NLB_DEV void norm2_range(Norm2& acc, const double* a, int i0, int i1) {
+    int i = i0;
+    for (; i + 7 <= i1; i += 7) {
+        double t[7];
+#pragma unroll
+        for (int u = 0; u < 7; ++u) t[u] = a[i + u];
+#pragma unroll
+        for (int u = 0; u < 7; ++u) acc.add(t[u]);
+    }
+    for (; i < i1; ++i) acc.add(a[i]);
+}
+
+// Short register vectors: the plain two-branch form of the same recurrence is slightly faster there
+// (measured on the 2x2 Broyden kernel), the select form wins in the long local-memory loops of LM.
 template <int N>
 NLB_DEV double norm2_vec(const double (&v)[N]) {
-    Norm2 acc;
+    double scale = 1.0, ssq = 0.0;
 #pragma unroll
-    for (int i = 0; i < N; ++i) acc.add(v[i]);
-    return acc.value();
+    for (int i = 0; i < N; ++i) {
+        const double x = v[i];
+        if (x != 0.0) {
+            const double a = fabs(x);
+            if (scale < a) {
+                const double t = scale / a;
+                ssq = 1.0 + ssq * t * t;
+                scale = a;
+            } else {
+                const double t = a / scale;
+                ssq += t * t;
+            }
+        }
+    }
+    return scale * sqrt(ssq);
 }
 
 template <int N>
@@ -211,6 +255,18 @@ NLB_DEV double dlapy2(double x, double y) {
     return w * sqrt(1.0 + q * q);
 }
 
+// DLARTG's scaled branch (|f| or |g| outside [2^-511, 2^510.5]): rare, kept out of line.
+static __device__ __noinline__ void dlartg_scaled(double f, double g, double& c, double& s, double& r) {
+    const double safmin = 0x1p-1022, safmax = 0x1p1022;
+    const double u = nl_min(safmax, nl_max(safmin, nl_max(fabs(f), fabs(g))));
+    const double fs = f / u, gs = g / u;
+    const double d = sqrt(fs * fs + gs * gs);
+    c = fabs(fs) / d;
+    r = nl_sign(d, f);
+    s = gs / r;
+    r = r * u;
+}
+
 // DLARTG: c*f + s*g = r, -s*f + c*g = 0
 NLB_DEV void dlartg(double f, double g, double& c, double& s, double& r) {
     const double safmin = 0x1p-1022;
@@ -228,13 +284,7 @@ NLB_DEV void dlartg(double f, double g, double& c, double& s, double& r) {
         r = nl_sign(d, f);
         s = g / r;
     } else {
-        const double u = nl_min(safmax, nl_max(safmin, nl_max(f1, g1)));
-        const double fs = f / u, gs = g / u;
-        const double d = sqrt(fs * fs + gs * gs);
-        c = fabs(fs) / d;
-        r = nl_sign(d, f);
-        s = gs / r;
-        r = r * u;
+        dlartg_scaled(f, g, c, s, r);
     }
 }
 

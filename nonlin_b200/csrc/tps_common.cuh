@@ -114,14 +114,20 @@ NLB_DEV double backtrack_min(int mode, double f0, double f, double f1, double al
         const double rhs2 = f1 - f0 - alam1 * slope;
         const double a = (rhs1 / (alam * alam) - rhs2 / (alam1 * alam1)) / (alam - alam1);
         const double b = (-(alam1 * rhs1 / (alam * alam)) + alam * rhs2 / (alam1 * alam1)) / (alam - alam1);
-        if (a == 0.0) {
-            lam = -slope / (2.0 * b);
-        } else {
+        // the three quotient forms of the cubic model share one division
+        double num = -slope, den = 2.0 * b;
+        bool divide = true;
+        if (a != 0.0) {
             const double disc = b * b - 3.0 * a * slope;
-            if (disc < 0.0) lam = 0.5 * alam;
-            else if (b <= 0.0) lam = (-b + sqrt(disc)) / (3.0 * a);
-            else lam = -slope / (b + sqrt(disc));
+            if (disc < 0.0) {
+                divide = false;
+            } else {
+                const double sq = sqrt(disc);
+                if (b <= 0.0) { num = -b + sq; den = 3.0 * a; }
+                else { den = b + sq; }
+            }
         }
+        lam = divide ? num / den : 0.5 * alam;
         if (lam > 0.5 * alam) lam = 0.5 * alam;
     }
     return lam;

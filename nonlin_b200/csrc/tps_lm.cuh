@@ -15,7 +15,11 @@
 
 namespace nlb {
 
-#define NLB_UNROLL_M _Pragma("unroll(M <= 8 ? M : 1)")
+#ifndef NLB_UNROLL_M_FACTOR
+#define NLB_UNROLL_M_FACTOR 1   // measured on B200: 7 raises the 21x4 kernel to 206 registers and costs 30 %
+#endif
+constexpr int kUnrollM = NLB_UNROLL_M_FACTOR;   // unroll factor of the loops over the m equations of tall systems
+#define NLB_UNROLL_M _Pragma("unroll(M <= 8 ? M : kUnrollM)")
 
 // Pivoted Householder QR in place (MINPACK QRFAC lineage).  ipvt is 0-based.
 template <int M, int N>
@@ -125,14 +129,13 @@ NLB_DEV void lm_qrsolve(double (&a)[M * N], const int (&ipvt)[N], const double (
                 if (sdiag[k] == 0.0) continue;
                 double cs, sn;
                 const double rkk = a[k + k * M];
-                if (fabs(rkk) < fabs(sdiag[k])) {
-                    const double ctan = rkk / sdiag[k];
-                    sn = 0.5 / sqrt(0.25 + 0.25 * (ctan * ctan));
-                    cs = sn * ctan;
-                } else {
-                    const double tn = sdiag[k] / rkk;
-                    cs = 0.5 / sqrt(0.25 + 0.25 * (tn * tn));
-                    sn = cs * tn;
+                {   // both cases of the reference's rotation share one quotient, one sqrt and one division
+                    const bool small_r = fabs(rkk) < fabs(sdiag[k]);
+                    const double q = (small_r ? rkk : sdiag[k]) / (small_r ? sdiag[k] : rkk);   // ctan or tan
+                    const double v = 0.5 / sqrt(0.25 + 0.25 * (q * q));
+                    const double vq = v * q;
+                    sn = small_r ? v : vq;
+                    cs = small_r ? vq : v;
                 }
                 a[k + k * M] = cs * rkk + sn * sdiag[k];
                 double temp = cs * wa[k] + sn * qtbpj;

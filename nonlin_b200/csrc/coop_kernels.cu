@@ -64,15 +64,27 @@ int launch_lm(const DevParams& p, long long ntot, long long B, int m, double* x,
     long long chunk = (long long)((8ull << 30) / per_sys) / 32 * 32;
     if (chunk < 32) chunk = 32;
     if (chunk > ntot) chunk = (ntot + 31) / 32 * 32;
-    double* ws = nullptr;
-    if (cudaMallocAsync((void**)&ws, per_sys * (size_t)chunk, s) != cudaSuccess) return NLB_ERR_CUDA;
-    for (long long b0 = 0; b0 < ntot; b0 += chunk) {
-        const long long nsys = (ntot - b0 < chunk) ? (ntot - b0) : chunk;
-        const unsigned grid = (unsigned)((nsys + 31) / 32);
-        coop_lm_kernel<F, N><<<grid, 32 * N, S::BYTES, s>>>(p, B, b0, nsys, m, x, fvec, sys, shared, ib, status, ws);
-        ++*launches;
-        if (cudaGetLastError() != cudaSuccess) { cudaFreeAsync(ws, s); return NLB_ERR_CUDA; }
+    // Persistent CTAs: only as many as are resident at once; their 32 lanes pull systems from a cursor,
+    // so the HBM workspace is sized by the resident lanes, not by the batch.
+    static int ctas_per_sm = 0, num_sms = 0;
+    if (ctas_per_sm == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, coop_lm_kernel<F, N>, 32 * N, S::BYTES) != cudaSuccess)
+            return NLB_ERR_CUDA;
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
     }
+    long long grid = (ntot + 31) / 32;
+    if (grid > (long long)num_sms * ctas_per_sm) grid = (long long)num_sms * ctas_per_sm;
+    (void)chunk;
+    double* ws = nullptr;
+    if (cudaMallocAsync((void**)&ws, per_sys * 32 * (size_t)grid + 64, s) != cudaSuccess) return NLB_ERR_CUDA;
+    unsigned long long* cursor = reinterpret_cast<unsigned long long*>(ws + (size_t)(N + 2) * m * 32 * (size_t)grid);
+    if (cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), s) != cudaSuccess) { cudaFreeAsync(ws, s); return NLB_ERR_CUDA; }
+    coop_lm_kernel<F, N><<<(unsigned)grid, 32 * N, S::BYTES, s>>>(p, B, 0, ntot, m, x, fvec, sys, shared, ib, status, ws, cursor);
+    ++*launches;
+    if (cudaGetLastError() != cudaSuccess) { cudaFreeAsync(ws, s); return NLB_ERR_CUDA; }
     if (cudaFreeAsync(ws, s) != cudaSuccess) return NLB_ERR_CUDA;
     return NLB_OK;
 }

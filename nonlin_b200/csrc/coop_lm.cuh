@@ -30,12 +30,13 @@
 
 namespace nlb {
 
-enum { CLM_NEED_JAC = 0, CLM_INNER = 1, CLM_DONE = 2 };
+// lane states: a lane holds one system at a time and takes the next one from a work queue when it is done
+enum { CLM_NEED_JAC = 0, CLM_INNER = 1, CLM_DONE = 2, CLM_EMPTY = 3, CLM_NEW = 4, CLM_EXIT = 5 };
 
 template <int N>
 struct CoopLmSmem {
     static constexpr int NDV = 7 * N + N * N + 12;   // doubles per system
-    static constexpr int NIV = 2 * N + 10;           // ints per system
+    static constexpr int NIV = 2 * N + 12;           // ints per system
     static constexpr size_t BYTES = 32 * ((size_t)NDV * sizeof(double) + (size_t)NIV * sizeof(int));
 };
 
@@ -225,19 +226,17 @@ NLB_DEV void clm_par(const LaneMat<N>& r, const LaneIVec& ipvt, const LaneVec& d
 
 // scalar slots of a system in shared memory
 enum { SC_FNORM = 0, SC_PAR, SC_XNORM, SC_DELTA, SC_GNORM, SC_AJNORM, SC_AJJ, SC_PNORM, SC_TEMP, SC_H, SC_NSC = 12 };
-enum { SI_STATE = 0, SI_ITER, SI_NEVAL, SI_NJAC, SI_FLAG, SI_FCN, SI_XCN, SI_GCN, SI_PIVOT, SI_ACCEPT, SI_NSI = 10 };
+enum { SI_STATE = 0, SI_ITER, SI_NEVAL, SI_NJAC, SI_FLAG, SI_FCN, SI_XCN, SI_GCN, SI_PIVOT, SI_ACCEPT, SI_SYS, SI_NSI = 12 };
 
 template <class F, int N>
 __global__ void __launch_bounds__(32 * N)
 coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, double* __restrict__ xg,
                double* __restrict__ fg, const double* __restrict__ sys, const double* __restrict__ shared,
-               nlb_iteration_behavior* __restrict__ ibg, int32_t* __restrict__ statusg, double* __restrict__ ws) {
+               nlb_iteration_behavior* __restrict__ ibg, int32_t* __restrict__ statusg, double* __restrict__ ws,
+               unsigned long long* __restrict__ cursor) {
     static_assert(F::N == N, "residual / kernel size mismatch");
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
-    const long long loc = (long long)blockIdx.x * 32 + lane;
-    const bool valid = loc < nsys;
-    const long long b = b0 + (valid ? loc : 0);
 
     // shared memory carve-up: [element][lane]
     double* sd = smem + lane;
@@ -252,37 +251,74 @@ coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, do
     double* J = ws + (long long)blockIdx.x * gstride + lane;        // J(i, c) = J[(i*N + c)*32]
     double* fv = J + (long long)m * N * 32;                         // fvec(i) = fv[i*32]
     double* w4 = fv + (long long)m * 32;                            // wa4(i)  = w4[i*32]
-    const double* ysys = sys + b;                                   // y(i)    = ysys[i*B]
 
     const double eps = 0x1p-52;
     const double ftol = p.fcn_tol, xtol = p.var_tol, gtol = p.grad_tol, fac = p.lm_factor;
 
-    // ---- phase 0: load x, fvec = F(x), fnorm --------------------------------------------
-    if (k == 0) {
-        si[SI_STATE] = valid ? CLM_NEED_JAC : CLM_DONE;
-        si[SI_ITER] = 1; si[SI_NEVAL] = 1; si[SI_NJAC] = 0; si[SI_FLAG] = 0;
-        si[SI_FCN] = 0; si[SI_XCN] = 0; si[SI_GCN] = 0; si[SI_ACCEPT] = 0;
-        sc[SC_PAR] = 0.0; sc[SC_XNORM] = 0.0; sc[SC_DELTA] = 0.0; sc[SC_GNORM] = 0.0;
-    }
-    x[k] = valid ? xg[(long long)k * B + b] : 0.0;
-    __syncthreads();
-    if (valid) {
-        double xl[N];
-#pragma unroll
-        for (int j = 0; j < N; ++j) xl[j] = x[j];
-        for (int i = k; i < m; i += N) fv[(long long)i * 32] = F::residual(xl, __ldg(shared + i), ysys[(long long)i * B]);
-    }
-    __syncthreads();
-    if (k == 0 && valid) {
-        Norm2 acc;
-        clm_norm2_strided(acc, fv, 32, 0, m);
-        sc[SC_FNORM] = acc.value();
-    }
+    if (k == 0) { si[SI_STATE] = CLM_EMPTY; si[SI_SYS] = 0; si[SI_ACCEPT] = 0; }
     __syncthreads();
 
     for (;;) {
+        // ---- retire finished systems, take new ones from the queue ---------------------------
+        int st = si[SI_STATE];
+        if (st == CLM_DONE) {
+            const long long bo = b0 + si[SI_SYS];
+            xg[(long long)k * B + bo] = x[k];
+            for (int i = k; i < m; i += N) fg[(long long)i * B + bo] = fv[(long long)i * 32];
+            if (k == 0) {
+                if (ibg) {
+                    nlb_iteration_behavior o;
+                    o.iter_count = si[SI_ITER]; o.fcn_count = si[SI_NEVAL]; o.jacobian_count = si[SI_NJAC]; o.gradient_count = 0;
+                    o.converge_on_fcn = si[SI_FCN]; o.converge_on_chng = si[SI_XCN]; o.converge_on_zero_diff = si[SI_GCN];
+                    ibg[bo] = o;
+                }
+                if (statusg) statusg[bo] = si[SI_FLAG] != 0 ? NLB_CONVERGENCE_ERROR : NLB_NO_ERROR;
+            }
+        }
+        __syncthreads();
+        if (k == 0 && (st == CLM_DONE || st == CLM_EMPTY)) {
+            // one atomic per warp for all lanes that need a system
+            const unsigned mask = __activemask();
+            const int leader = __ffs(mask) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(cursor, (unsigned long long)__popc(mask));
+            base = __shfl_sync(mask, base, leader);
+            const long long idx = (long long)(base + __popc(mask & ((1u << lane) - 1u)));
+            if (idx < nsys) {
+                si[SI_SYS] = (int)idx;
+                si[SI_STATE] = CLM_NEW;
+                si[SI_ITER] = 1; si[SI_NEVAL] = 1; si[SI_NJAC] = 0; si[SI_FLAG] = 0;
+                si[SI_FCN] = 0; si[SI_XCN] = 0; si[SI_GCN] = 0; si[SI_ACCEPT] = 0;
+                sc[SC_PAR] = 0.0; sc[SC_XNORM] = 0.0; sc[SC_DELTA] = 0.0; sc[SC_GNORM] = 0.0;
+            } else {
+                si[SI_STATE] = CLM_EXIT;
+            }
+        }
+        __syncthreads();
+        st = si[SI_STATE];
+        if (__syncthreads_and(st == CLM_EXIT)) break;
+        const long long b = b0 + si[SI_SYS];
+        const double* ysys = sys + b;                               // y(i) = ysys[i*B]
+
+        // ---- new system: load x, fvec = F(x), fnorm ------------------------------------------
+        if (st == CLM_NEW) x[k] = xg[(long long)k * B + b];
+        __syncthreads();
+        if (st == CLM_NEW) {
+            double xl[N];
+#pragma unroll
+            for (int j = 0; j < N; ++j) xl[j] = x[j];
+            for (int i = k; i < m; i += N) fv[(long long)i * 32] = F::residual(xl, __ldg(shared + i), ysys[(long long)i * B]);
+        }
+        __syncthreads();
+        if (st == CLM_NEW && k == 0) {
+            Norm2 acc;
+            clm_norm2_strided(acc, fv, 32, 0, m);
+            sc[SC_FNORM] = acc.value();
+            si[SI_STATE] = CLM_NEED_JAC;
+        }
+        __syncthreads();
+
         const int state0 = si[SI_STATE];
-        if (__syncthreads_and(state0 == CLM_DONE)) break;
         const bool needjac = state0 == CLM_NEED_JAC;
 
         // ---- phase J: forward-difference column k, its norm (vfh_jac_fcn :262-275, lmfactor :611-616)
@@ -499,7 +535,7 @@ coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, do
         __syncthreads();
 
         // ---- phases G + P on warp 0: scaling, gradient test, LM parameter, trial point --------
-        if (k == 0 && state0 != CLM_DONE) {
+        if (k == 0 && (state0 == CLM_NEED_JAC || state0 == CLM_INNER)) {
             int state = state0;
             const int iter = si[SI_ITER];
             const double fnorm = sc[SC_FNORM];
@@ -658,20 +694,6 @@ coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, do
         if (k == 0) si[SI_ACCEPT] = 0;
     }
 
-    // ---- results ---------------------------------------------------------------------------
-    if (valid) {
-        xg[(long long)k * B + b] = x[k];
-        for (int i = k; i < m; i += N) fg[(long long)i * B + b] = fv[(long long)i * 32];
-        if (k == 0) {
-            if (ibg) {
-                nlb_iteration_behavior o;
-                o.iter_count = si[SI_ITER]; o.fcn_count = si[SI_NEVAL]; o.jacobian_count = si[SI_NJAC]; o.gradient_count = 0;
-                o.converge_on_fcn = si[SI_FCN]; o.converge_on_chng = si[SI_XCN]; o.converge_on_zero_diff = si[SI_GCN];
-                ibg[b] = o;
-            }
-            if (statusg) statusg[b] = si[SI_FLAG] != 0 ? NLB_CONVERGENCE_ERROR : NLB_NO_ERROR;
-        }
-    }
 }
 
 int launch_coop_lm(int fcn_id, const DevParams& p, long long nsys, long long B, int m, int n, double* x, double* fvec, const double* sys,

@@ -58,9 +58,9 @@ int launch_lm(const DevParams& p, long long ntot, long long B, int m, double* x,
             return NLB_ERR_CUDA;
         configured = true;
     }
-    // HBM workspace: (n + 2) * m doubles per system, allocated stream-ordered and capped at 8 GiB
+    // HBM workspace: (n + 3) * m doubles per resident lane, allocated stream-ordered and capped at 8 GiB
     // per launch; larger batches run as consecutive launches over contiguous system ranges.
-    const size_t per_sys = (size_t)(N + 2) * (size_t)m * sizeof(double);
+    const size_t per_sys = (size_t)(N + 3) * (size_t)m * sizeof(double);
     long long chunk = (long long)((8ull << 30) / per_sys) / 32 * 32;
     if (chunk < 32) chunk = 32;
     if (chunk > ntot) chunk = (ntot + 31) / 32 * 32;
@@ -80,7 +80,7 @@ int launch_lm(const DevParams& p, long long ntot, long long B, int m, double* x,
     (void)chunk;
     double* ws = nullptr;
     if (cudaMallocAsync((void**)&ws, per_sys * 32 * (size_t)grid + 64, s) != cudaSuccess) return NLB_ERR_CUDA;
-    unsigned long long* cursor = reinterpret_cast<unsigned long long*>(ws + (size_t)(N + 2) * m * 32 * (size_t)grid);
+    unsigned long long* cursor = reinterpret_cast<unsigned long long*>(ws + (size_t)(N + 3) * m * 32 * (size_t)grid);
     if (cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), s) != cudaSuccess) { cudaFreeAsync(ws, s); return NLB_ERR_CUDA; }
     coop_lm_kernel<F, N><<<(unsigned)grid, 32 * N, S::BYTES, s>>>(p, B, 0, ntot, m, x, fvec, sys, shared, ib, status, ws, cursor);
     ++*launches;

@@ -40,6 +40,11 @@ struct CoopLmSmem {
     static constexpr size_t BYTES = 32 * ((size_t)NDV * sizeof(double) + (size_t)NIV * sizeof(int));
 };
 
+// L2 prefetch of a line that a later batch of the same sequential pass will load (turns an HBM round
+// trip per batch into an L2 hit)
+NLB_DEV void clm_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+constexpr int CLM_PF = 48;   // rows ahead
+
 // per-lane views into [element][32] shared arrays
 struct LaneVec {
     double* p;
@@ -75,6 +80,104 @@ NLB_DEV void clm_norm2_strided(Norm2& acc, const double* __restrict__ v, long lo
         for (int u = 0; u < 8; ++u) acc.add(t[u]);
     }
     for (; i < i1; ++i) acc.add(v[(long long)i * stride]);
+}
+
+// libgfortran NORM2 of v[i0..i1) (element i at v[i*stride]) evaluated by the N threads of a system with the
+// SAME result as the one-thread recurrence:
+//   1. thread k finds max|v| of its contiguous chunk                       (parallel, exact)
+//   2. the scale entering chunk k is max(1, maxima of the earlier chunks): exactly the running scale
+//      of the sequential algorithm, which only ever grows to the largest magnitude seen so far
+//   3. thread k forms, for each of its elements, the quotient the recurrence would form (scale/a when
+//      the element raises the scale, a/scale otherwise) and stores it in tq, negated in the first case
+//                                                                            (parallel: all divisions)
+//   4. the leader replays ssq = 1 + ssq*t*t  /  ssq += t*t over tq in index order (sequential, cheap)
+// All threads of the CTA must call this (three barriers); `on` = the lane takes part.
+template <int N>
+NLB_DEV double clm_coop_norm2(bool on, const double* __restrict__ v, long long stride, int i0, int i1,
+                              double* __restrict__ tq, const LaneVec& cmax, int k, bool leader) {
+    const int L = i1 - i0;
+    const int len = (L + N - 1) / N;
+    const int c0 = i0 + k * len;
+    const int c1 = (c0 + len < i1) ? c0 + len : i1;
+    if (on) {
+        double mx = 0.0;
+        int i = c0;
+        for (; i + 4 <= c1; i += 4) {
+            double t[4];
+            if (i + CLM_PF + 4 <= c1) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) clm_prefetch(&v[(long long)(i + CLM_PF + u) * stride]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) t[u] = fabs(v[(long long)(i + u) * stride]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (t[u] > mx) mx = t[u];
+        }
+        for (; i < c1; ++i) { const double a = fabs(v[(long long)i * stride]); if (a > mx) mx = a; }
+        cmax[k] = mx;
+    }
+    __syncthreads();
+    if (on) {
+        double sc = 1.0;
+        for (int c = 0; c < k; ++c) { const double a = cmax[c]; if (sc < a) sc = a; }
+        int i = c0;
+        for (; i + 4 <= c1; i += 4) {
+            double x[4], q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) x[u] = v[(long long)(i + u) * stride];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                q[u] = 0.0;
+                if (x[u] != 0.0) {
+                    const double a = fabs(x[u]);
+                    const bool up = sc < a;
+                    const double t = (up ? sc : a) / (up ? a : sc);
+                    q[u] = up ? -fmax(t, 4.9406564584124654e-324) : t;
+                    sc = up ? a : sc;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) tq[(long long)(i + u) * 32] = q[u];
+        }
+        for (; i < c1; ++i) {
+            const double x = v[(long long)i * stride];
+            double q = 0.0;
+            if (x != 0.0) {
+                const double a = fabs(x);
+                const bool up = sc < a;
+                const double t = (up ? sc : a) / (up ? a : sc);
+                q = up ? -fmax(t, 4.9406564584124654e-324) : t;
+                sc = up ? a : sc;
+            }
+            tq[(long long)i * 32] = q;
+        }
+    }
+    __syncthreads();
+    double result = 0.0;
+    if (on && leader) {
+        double scale = 1.0;
+        for (int c = 0; c < N; ++c) { const double a = cmax[c]; if (scale < a) scale = a; }
+        double ssq = 0.0;
+        int i = i0;
+        for (; i + 8 <= i1; i += 8) {
+            double q[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) q[u] = tq[(long long)(i + u) * 32];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (q[u] < 0.0) { const double t = -q[u]; ssq = 1.0 + ssq * t * t; }
+                else ssq = ssq + q[u] * q[u];
+            }
+        }
+        for (; i < i1; ++i) {
+            const double q = tq[(long long)i * 32];
+            if (q < 0.0) { const double t = -q; ssq = 1.0 + ssq * t * t; }
+            else ssq = ssq + q * q;
+        }
+        result = scale * sqrt(ssq);
+    }
+    __syncthreads();
+    return result;
 }
 
 // lmsolve on the n x n block held in shared memory (strict lower triangle = scratch for S^T).
@@ -247,10 +350,11 @@ coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, do
     const LaneIVec ipvt{si_base}, pos{si_base + 32 * N}, si{si_base + 64 * N};
 
     // HBM workspace of this group
-    const long long gstride = (long long)(N + 2) * m * 32;
+    const long long gstride = (long long)(N + 3) * m * 32;
     double* J = ws + (long long)blockIdx.x * gstride + lane;        // J(i, c) = J[(i*N + c)*32]
     double* fv = J + (long long)m * N * 32;                         // fvec(i) = fv[i*32]
     double* w4 = fv + (long long)m * 32;                            // wa4(i)  = w4[i*32]
+    double* tq = w4 + (long long)m * 32;                            // quotient scratch of the cooperative norms
 
     const double eps = 0x1p-52;
     const double ftol = p.fcn_tol, xtol = p.var_tol, gtol = p.grad_tol, fac = p.lm_factor;
@@ -310,11 +414,12 @@ coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, do
             for (int i = k; i < m; i += N) fv[(long long)i * 32] = F::residual(xl, __ldg(shared + i), ysys[(long long)i * B]);
         }
         __syncthreads();
-        if (st == CLM_NEW && k == 0) {
-            Norm2 acc;
-            clm_norm2_strided(acc, fv, 32, 0, m);
-            sc[SC_FNORM] = acc.value();
-            si[SI_STATE] = CLM_NEED_JAC;
+        {
+            const double fn = clm_coop_norm2<N>(st == CLM_NEW, fv, 32, 0, m, tq, w4h, k, k == 0);
+            if (st == CLM_NEW && k == 0) {
+                sc[SC_FNORM] = fn;
+                si[SI_STATE] = CLM_NEED_JAC;
+            }
         }
         __syncthreads();
 
@@ -383,13 +488,14 @@ coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, do
                 si[SI_PIVOT] = ipvt[j];
             }
             __syncthreads();
-            if (needjac && k == si[SI_PIVOT]) {
-                // ajnorm = norm2(a(j:m, pivot)): strictly sequential, one thread
-                Norm2 acc;
-                clm_norm2_strided(acc, J + k * 32, (long long)N * 32, j, m);
-                double ajnorm = acc.value();
-                if (ajnorm != 0.0 && J[((long long)j * N + k) * 32] < 0.0) ajnorm = -ajnorm;
-                sc[SC_AJNORM] = ajnorm;
+            {
+                // ajnorm = norm2(a(j:m, pivot)), all threads of the system cooperating (bit-identical to the scan)
+                const int pc = si[SI_PIVOT];
+                double ajnorm = clm_coop_norm2<N>(needjac, J + pc * 32, (long long)N * 32, j, m, tq, w4h, k, k == 0);
+                if (needjac && k == 0) {
+                    if (ajnorm != 0.0 && J[((long long)j * N + pc) * 32] < 0.0) ajnorm = -ajnorm;
+                    sc[SC_AJNORM] = ajnorm;
+                }
             }
             __syncthreads();
             if (needjac && sc[SC_AJNORM] != 0.0) {
@@ -406,12 +512,13 @@ coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, do
                     for (int u = 0; u < 4; ++u) t[u] = t[u] / ajnorm;
                     if (i == j) { t[0] = t[0] + 1.0; sc[SC_AJJ] = t[0]; }      // a(j,j) = a(j,j)/ajnorm + 1
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) col[(i + u * N) * rs] = t[u];
+                    for (int u = 0; u < 4; ++u) { col[(i + u * N) * rs] = t[u]; tq[(long long)(i + u * N) * 32] = t[u]; }
                 }
                 for (; i < m; i += N) {
                     double t = col[i * rs] / ajnorm;
                     if (i == j) { t = t + 1.0; sc[SC_AJJ] = t; }
                     col[i * rs] = t;
+                    tq[(long long)i * 32] = t;      // lane-contiguous copy of the reflector for the passes below
                 }
             }
             __syncthreads();
@@ -420,32 +527,43 @@ coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, do
                 const double ajnorm = sc[SC_AJNORM];
                 const int mypos = pos[k];
                 if (mypos > j && ajnorm != 0.0) {
-                    const double* __restrict__ cp = J + pc * 32;     // pivot column (read only here)
-                    double* __restrict__ ck = J + k * 32;            // own column, pc != k
+                    // The reflector is read from its lane-contiguous copy in tq: every warp of the CTA then loads
+                    // the same fully coalesced 256 B per row (L1 hits), instead of 32 scattered sectors of J.
+                    const double* __restrict__ cp = tq;              // reflector v(i) = cp[i * 32]
+                    double* __restrict__ ck = J + k * 32;            // own column
                     const long long rs = (long long)N * 32;
+                    (void)pc;
                     double sm = 0.0;
                     {
                         int i = j;
                         for (; i + 8 <= m; i += 8) {
                             double a[8], c[8];
+                            if (i + CLM_PF + 8 <= m) {
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) { a[u] = cp[(i + u) * rs]; c[u] = ck[(i + u) * rs]; }
+                                for (int u = 0; u < 8; ++u) clm_prefetch(&ck[(i + CLM_PF + u) * rs]);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) { a[u] = cp[(long long)(i + u) * 32]; c[u] = ck[(i + u) * rs]; }
 #pragma unroll
                             for (int u = 0; u < 8; ++u) sm += a[u] * c[u];
                         }
-                        for (; i < m; ++i) sm += cp[i * rs] * ck[i * rs];
+                        for (; i < m; ++i) sm += cp[(long long)i * 32] * ck[i * rs];
                     }
                     double temp = sm / sc[SC_AJJ];
                     {
                         int i = j;
                         for (; i + 8 <= m; i += 8) {
                             double a[8], c[8];
+                            if (i + CLM_PF + 8 <= m) {
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) { a[u] = cp[(i + u) * rs]; c[u] = ck[(i + u) * rs]; }
+                                for (int u = 0; u < 8; ++u) clm_prefetch(&ck[(i + CLM_PF + u) * rs]);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) { a[u] = cp[(long long)(i + u) * 32]; c[u] = ck[(i + u) * rs]; }
 #pragma unroll
                             for (int u = 0; u < 8; ++u) ck[(i + u) * rs] = c[u] - temp * a[u];
                         }
-                        for (; i < m; ++i) ck[i * rs] = ck[i * rs] - temp * cp[i * rs];
+                        for (; i < m; ++i) ck[i * rs] = ck[i * rs] - temp * cp[(long long)i * 32];
                     }
                     double rd = wa1[mypos];
                     if (rd != 0.0) {
@@ -495,6 +613,10 @@ coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, do
                         int i = j;
                         for (; i + 8 <= m; i += 8) {
                             double a[8], c[8];
+                            if (i + CLM_PF + 8 <= m) {
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) { clm_prefetch(&col[(i + CLM_PF + u) * rs]); clm_prefetch(&w4[(long long)(i + CLM_PF + u) * 32]); }
+                            }
 #pragma unroll
                             for (int u = 0; u < 8; ++u) { a[u] = col[(i + u) * rs]; c[u] = w4[(long long)(i + u) * 32]; }
 #pragma unroll
@@ -609,6 +731,10 @@ coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, do
         }
         __syncthreads();
 
+        {
+            const double f1n = clm_coop_norm2<N>(inner, w4, 32, 0, m, tq, w4h, k, k == 0);
+            if (inner && k == 0) sc[SC_TEMP] = f1n;
+        }
         // ---- phase A on warp 0: gain ratio, step bound, acceptance, convergence (lss_solve :297-365)
         if (k == 0 && inner) {
             int iter = si[SI_ITER];
@@ -616,12 +742,7 @@ coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, do
             si[SI_NEVAL] = neval;
             double fnorm = sc[SC_FNORM], par = sc[SC_PAR], delta = sc[SC_DELTA], xnorm = sc[SC_XNORM];
             const double pnorm = sc[SC_PNORM], gnorm = sc[SC_GNORM];
-            double fnorm1;
-            {
-                Norm2 acc;
-                clm_norm2_strided(acc, w4, 32, 0, m);
-                fnorm1 = acc.value();
-            }
+            const double fnorm1 = sc[SC_TEMP];
             double actred = -1.0;
             if (0.1 * fnorm1 < fnorm) { const double q = fnorm1 / fnorm; actred = 1.0 - q * q; }
             double temp = 0.0;

@@ -9,7 +9,7 @@ B = 2^20 systems per GPU (inputs already resident in HBM) followed by the statis
 that counts the converged systems.  The default workload is BASELINE.json configs[1]:
 1M x README Example 1 (2x2, quasi_newton_solver, perturbed x0).  With N GPUs every rank solves
 its own 2^20-system shard (weak scaling, no data-path collective); the per-rank statistics are
-combined with one 128-byte all-gather per step.
+combined with one 128-byte all-gather at the end of the job (inside the timed region).
 
 One JSON line is printed by rank 0 (schema: the bench contract in the task description).
   value      converged systems / s, all ranks, device-resident inputs, CUDA-event time (max over ranks)
@@ -241,10 +241,6 @@ class DeviceRun:
     def step(self, k, dist_on):
         self.solver.solve(self.obj, self.xs[k], self.f, self.ib, args=self.args, status=self.status)
         self.eng.reduce_stats_device(self.ib, self.status, self.stats, self.B)
-        if dist_on:
-            from nonlin_b200.distributed import allreduce_stats
-
-            allreduce_stats(self.stats)
 
     def timed(self, steps, warmup, dist_on, sampler=None):
         torch = self.torch
@@ -269,7 +265,8 @@ class DeviceRun:
             self.solver.solve(self.obj, self.xs[warmup + k], self.f, self.ib, args=self.args, status=self.status)
             es[k].record()                             # end of the dominant (solve) kernel
             self.eng.reduce_stats_device(self.ib, self.status, self.stats, self.B)
-            if dist_on:
+            if dist_on and k == steps - 1:
+                # the one collective of the path: the final convergence-statistics reduction of the job
                 from nonlin_b200.distributed import allreduce_stats
 
                 allreduce_stats(self.stats)
@@ -394,7 +391,9 @@ def run_engine(args):
         except Exception:
             traffic = None
     roofline = {
-        "bound": "fp64", "kernel": "tps_solve_kernel" if w["name"] in ("C1", "C2", "C3") else "coop_solve_kernel",
+        "bound": "fp64", "kernel": {"C1": "tps_solve_kernel<LsqPolyFit, LM>", "C2": "tps_solve_kernel<Misc2Fcn, Broyden>",
+                                    "C3": "tps_newton_refill_kernel<PowellBadlyScaled>", "C4": "coop_lm_kernel<Rational78, 16>",
+                                    "C5": "coop_broyden_kernel<ExtRosenbrock, 64>", "LM4": "coop_lm_kernel<ExpDecay4, 4>"}[w["name"]],
         "achieved": achieved_tf, "peak": peak["dfma_tflops"], "unit": "TFLOP/s", "frac": achieved_tf / peak["dfma_tflops"],
         "peak_source": "DFMA micro-kernel measured on this GPU at run time (MEASURED_PEAKS.json has no FP64 entry)",
         "peak_no_fma": peak["dadd_dmul_tflops"], "frac_of_no_fma_peak": achieved_tf / peak["dadd_dmul_tflops"],
@@ -408,7 +407,7 @@ def run_engine(args):
 
     extras = {}
     if not args.no_extras and world == 1:
-        for name in ("C1", "C3"):
+        for name in ("C1", "C3", "C5", "LM4"):
             if name == args.workload:
                 continue
             try:

@@ -48,6 +48,53 @@ __global__ void rosenbrock_eval_kernel(long long B, int n, const double* __restr
     }
 }
 
+// vecfcn_helper%jacobian for the curve-fit families: thread (b, j) forms column j of system b,
+// jac[(i + j*m)*B + b] = (f_i(x + h e_j) - f_i(x)) / h   (vfh_jac_fcn, multi_eqn:257-275)
+template <class F>
+__global__ void curvefit_jacobian_kernel(long long B, int m, const double* __restrict__ x, double* __restrict__ jac,
+                                         const double* __restrict__ sys, const double* __restrict__ shared) {
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (b >= B) return;
+    double x0[F::N], x1[F::N];
+#pragma unroll
+    for (int c = 0; c < F::N; ++c) x0[c] = x[c * B + b];
+    double temp = 0.0;
+#pragma unroll
+    for (int c = 0; c < F::N; ++c) temp = (c == j) ? x0[c] : temp;
+    double h = 0x1p-26 * fabs(temp);
+    if (h == 0.0) h = 0x1p-26;
+#pragma unroll
+    for (int c = 0; c < F::N; ++c) x1[c] = (c == j) ? (temp + h) : x0[c];
+    for (int i = 0; i < m; ++i) {
+        const double t = __ldg(shared + i), y = sys[(long long)i * B + b];
+        jac[((long long)i + (long long)j * m) * B + b] = (F::residual(x1, t, y) - F::residual(x0, t, y)) / h;
+    }
+}
+
+__global__ void rosenbrock_jacobian_kernel(long long B, int n, const double* __restrict__ x, double* __restrict__ jac) {
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (b >= B) return;
+    // column j only touches the two equations of its pair; every other entry is (f - f)/h = 0 exactly
+    const int p0 = j & ~1;
+    const double xa = x[(long long)p0 * B + b], xb = x[(long long)(p0 + 1) * B + b];
+    const double temp = (j & 1) ? xb : xa;
+    double h = 0x1p-26 * fabs(temp);
+    if (h == 0.0) h = 0x1p-26;
+    const double xa1 = (j & 1) ? xa : temp + h, xb1 = (j & 1) ? temp + h : xb;
+    for (int i = 0; i < n; ++i) {
+        double v = 0.0;
+        if (i == p0) v = (10.0 * (xb1 - xa1 * xa1) - 10.0 * (xb - xa * xa)) / h;
+        else if (i == p0 + 1) v = ((1.0 - xa1) - (1.0 - xa)) / h;
+        else {
+            // (f_i(x + h e_j) - f_i(x)) / h with f_i independent of x_j: the difference of two equal values
+            v = 0.0 / h;
+        }
+        jac[((long long)i + (long long)j * n) * B + b] = v;
+    }
+}
+
 template <class F, int N>
 int launch_lm(const DevParams& p, long long ntot, long long B, int m, double* x, double* fvec, const double* sys, const double* shared,
               nlb_iteration_behavior* ib, int32_t* status, cudaStream_t s, int64_t* launches) {
@@ -128,6 +175,19 @@ int launch_coop_eval(int fcn_id, long long B, int m, int n, const double* x, dou
         case FCN_EXP_SUM_8: curvefit_eval_kernel<ExpSum8><<<grid, 128, 0, s>>>(B, m, x, fvec, sys, shared); break;
         case FCN_EXP_DECAY_4: curvefit_eval_kernel<ExpDecay4><<<grid, 128, 0, s>>>(B, m, x, fvec, sys, shared); break;
         case FCN_EXT_ROSENBROCK: rosenbrock_eval_kernel<<<dim3(gx, (unsigned)(n / 2 < 32 ? n / 2 : 32)), 128, 0, s>>>(B, n, x, fvec); break;
+        default: return NLB_ERR_UNSUPPORTED;
+    }
+    return NLB_OK;
+}
+
+int launch_coop_jacobian(int fcn_id, long long B, int m, int n, const double* x, double* jac, const double* sys,
+                         const double* shared, cudaStream_t s) {
+    const dim3 grid((unsigned)((B + 127) / 128), (unsigned)n);
+    switch (fcn_id) {
+        case FCN_RATIONAL_7_8: curvefit_jacobian_kernel<Rational78><<<grid, 128, 0, s>>>(B, m, x, jac, sys, shared); break;
+        case FCN_EXP_SUM_8: curvefit_jacobian_kernel<ExpSum8><<<grid, 128, 0, s>>>(B, m, x, jac, sys, shared); break;
+        case FCN_EXP_DECAY_4: curvefit_jacobian_kernel<ExpDecay4><<<grid, 128, 0, s>>>(B, m, x, jac, sys, shared); break;
+        case FCN_EXT_ROSENBROCK: rosenbrock_jacobian_kernel<<<grid, 128, 0, s>>>(B, n, x, jac); break;
         default: return NLB_ERR_UNSUPPORTED;
     }
     return NLB_OK;

@@ -14,4 +14,7 @@ int launch_coop_solve(int solver, int fcn_id, const DevParams& p, long long nsys
 int launch_coop_eval(int fcn_id, long long B, int m, int n, const double* x, double* fvec, const double* sys,
                      const double* shared, cudaStream_t s);
 
+int launch_coop_jacobian(int fcn_id, long long B, int m, int n, const double* x, double* jac, const double* sys,
+                         const double* shared, cudaStream_t s);
+
 }  // namespace nlb

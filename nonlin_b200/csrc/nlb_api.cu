@@ -623,7 +623,10 @@ int nlb_jacobian_batch(nlb_handle* h, const nlb_params* params, int fcn_id, int6
         break;
         NLB_FIXED_FCNS(X)
 #undef X
-        default: return set_err(h, NLB_ERR_UNSUPPORTED, "no Jacobian kernel for this residual");
+        default:
+            rc = launch_coop_jacobian(fcn_id, B, m, n, (const double*)ax.dev, (double*)aj.dev, (const double*)as.dev,
+                                      (const double*)ash.dev, s);
+            if (rc) return set_err(h, rc, "no Jacobian kernel for this residual");
     }
     ++h->launches;
     NLB_CUDA(h, cudaGetLastError());

@@ -439,3 +439,72 @@ def test_c4_full_m_sample(engine, oracle):
     xo, fo, ibo, sto = oracle.solve_batch(w["solver"], w["fcn"], w["x0"], m=4096, sys=w["args"], shared=w["shared"],
                                           params=oracle.params(max_fcn_evals=12))
     assert (sto != 0).any() and np.array_equal(st, sto) and np.array_equal(x, xo) and np.array_equal(ib, ibo)
+
+
+def test_runtime_family_jacobian(engine, oracle):
+    """vecfcn_helper%jacobian (forward differences) for the run-time sized residual families."""
+    import nonlin_b200 as nb
+    from nonlin_b200 import workloads as W
+
+    for w in (W.c4_lm_rational(40, m=96), W.lm_expdecay4(40, m=48), W.c5_broyden_rosenbrock(40, n=16)):
+        obj = nb.vecfcn_helper(); obj.set_fcn(w["fcn"], w["m"], w["n"])
+        if w["shared"] is not None:
+            obj.set_shared_data(w["shared"])
+        jac = obj.jacobian(w["x0"], args=w["args"])              # (n, m, B)
+        for b in (0, 13, 39):
+            jo = oracle.jacobian(w["fcn"], w["x0"][:, b], m=w["m"], sys=None if w["args"] is None else w["args"][:, b],
+                                 shared=w["shared"])
+            assert np.array_equal(jac[:, :, b].T, jo)
+
+
+SETTINGS = [
+    # (workload, solver setters, oracle params)
+    ("C2", {"set_fcn_tolerance": 1e-12, "set_var_tolerance": 1e-9}, {"fcn_tol": 1e-12, "var_tol": 1e-9}),
+    ("C2", {"set_jacobian_interval": 1}, {"jacobian_interval": 1}),
+    ("C2", {"set_jacobian_interval": 20, "set_max_fcn_evals": 9}, {"jacobian_interval": 20, "max_fcn_evals": 9}),
+    ("C2", {"set_use_line_search": False}, {"use_line_search": 0}),
+    ("C3", {"set_max_fcn_evals": 1000, "set_gradient_tolerance": 1e-3}, {"max_fcn_evals": 1000, "grad_tol": 1e-3}),
+    ("C3", {"set_max_fcn_evals": 30}, {"max_fcn_evals": 30}),
+    ("C3", {"set_max_fcn_evals": 1000, "set_use_line_search": False}, {"max_fcn_evals": 1000, "use_line_search": 0}),
+    ("C1", {"set_step_scaling_factor": 0.5}, {"lm_factor": 0.5}),
+    ("C1", {"set_fcn_tolerance": 1e-14, "set_var_tolerance": 1e-15, "set_gradient_tolerance": 0.0, "set_max_fcn_evals": 40},
+     {"fcn_tol": 1e-14, "var_tol": 1e-15, "grad_tol": 0.0, "max_fcn_evals": 40}),
+    ("C1", {"set_gradient_tolerance": 1e-2}, {"grad_tol": 1e-2}),
+    ("LM4", {"set_max_fcn_evals": 6, "set_step_scaling_factor": 1.0}, {"max_fcn_evals": 6, "lm_factor": 1.0}),
+    ("C5", {"set_jacobian_interval": 2, "set_fcn_tolerance": 1e-11}, {"jacobian_interval": 2, "fcn_tol": 1e-11}),
+]
+
+
+@pytest.mark.parametrize("case", SETTINGS, ids=lambda c: c[0] + "-" + "-".join(k[4:] for k in c[1]))
+def test_solver_settings_parity(engine, oracle, case):
+    """Every setter of the reference's solver objects reaches the kernels and changes the result exactly as it
+    changes the oracle's (tolerances, evaluation budget -> status 106, Jacobian interval, line search, LM factor)."""
+    import nonlin_b200 as nb
+    from nonlin_b200 import workloads as W
+
+    name, setters, oparams = case
+    B = {"C5": 24, "LM4": 300}.get(name, 2000)
+    w = W.WORKLOADS[name](B, **({"n": 32} if name == "C5" else {}))
+    w["settings"] = dict(setters)
+    x, f, ib, st = run_engine(nb, w)
+    xo, fo, ibo, sto = oracle.solve_batch(w["solver"], w["fcn"], w["x0"], m=w["m"], sys=w["args"], shared=w["shared"],
+                                          params=oracle.params(**oparams))
+    assert np.array_equal(st, sto) and np.array_equal(x, xo) and np.array_equal(f, fo) and np.array_equal(ib, ibo)
+
+
+def test_custom_line_search_object(engine, oracle):
+    """set_line_search(ls) with non-default alpha / distance factor / evaluation cap; a cap of 2 makes some line
+    searches fail -> NL_CONVERGENCE_ERROR from inside the line search, like the reference's `error stop`."""
+    import nonlin_b200 as nb
+    from nonlin_b200 import workloads as W
+
+    w = W.c3_newton_powell(3000)
+    for max_ev, alpha, fac in ((100, 1e-3, 0.5), (2, 1e-4, 0.1)):
+        ls = nb.line_search(); ls.set_max_fcn_evals(max_ev); ls.set_scaling_factor(alpha); ls.set_distance_factor(fac)
+        s = nb.newton_solver(); s.set_max_fcn_evals(1000); s.set_line_search(ls)
+        x, f, ib, st = run_engine(nb, w, solver=s)
+        xo, fo, ibo, sto = oracle.solve_batch("newton", w["fcn"], w["x0"],
+                                              params=oracle.params(max_fcn_evals=1000, ls_max_fcn_evals=max_ev, ls_alpha=alpha, ls_factor=fac))
+        assert np.array_equal(st, sto) and np.array_equal(x, xo) and np.array_equal(f, fo) and np.array_equal(ib, ibo)
+        if max_ev == 2:
+            assert (st == nb.NL_CONVERGENCE_ERROR).any()

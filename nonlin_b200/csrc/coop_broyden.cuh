@@ -5,10 +5,12 @@
 // calls (qr_factor, rank1_update, qr_rank1_update, mtx_mult, solve_triangular_system,
 // recip_mult_array) as the Reference-LAPACK / QRUPDATE algorithms listed in tps_dense.cuh.
 //
-// Mapping.  One CTA of N threads owns one system for its whole solve.  B, Q and R (N x N,
-// column-major, leading dimension N+1 so that both row-wise and column-wise sweeps are bank-
-// conflict free) and every vector live in shared memory: 3*N*(N+1)*8 B = 97.5 KB at N = 64,
-// two CTAs per SM.  HBM is touched once to read x0 and once to write x, fvec, ib, status.
+// Mapping.  One CTA of N threads owns one system for its whole solve.  Q and R (N x N, column-major,
+// leading dimension N+1 so that both row-wise and column-wise sweeps are bank-conflict free) and every
+// vector live in shared memory; the Broyden matrix B lives in REGISTERS, thread t holding row t (B is
+// only ever used row-wise - B*dx, the rank-1 update, the forward differences - except for B^T f, which
+// goes through a 4-row staging buffer).  73 KB of shared memory at N = 64: three CTAs per SM.  HBM is
+// touched once to read x0 and once to write x, fvec, ib, status.
 //
 // Parity.  Every sum keeps the index order of the reference's loop, so results are bit-identical
 // to the CPU oracle.  That is affordable because the O(n^2) kernels parallelise over the
@@ -26,8 +28,9 @@ template <int N>
 struct CoopBroydenSmem {
     static constexpr int LD = N + 1;
     static constexpr int MAT = N * LD;
-    static constexpr int NVEC = 14;
-    static constexpr size_t BYTES = (3 * (size_t)MAT + NVEC * (size_t)N) * sizeof(double);
+    static constexpr int NVEC = 10;
+    static constexpr int STAGE = 4;     // rows of B published at a time for B^T f
+    static constexpr size_t BYTES = (2 * (size_t)MAT + (NVEC + STAGE) * (size_t)N) * sizeof(double);
 };
 
 // ---- redundant sequential reductions (identical in every thread) -----------------------
@@ -95,9 +98,10 @@ NLB_DEV void cb_reflect_trailing(double* a, int i, double tau, int tid) {
 
 // qr_factor(b, q = q, r = r): DGEQR2 on a copy of B, R = upper triangle, Q by DORG2R.
 template <int N>
-NLB_DEV void cb_qr_full(const double* bm, double* q, double* r, double* tau, int tid) {
+NLB_DEV void cb_qr_full(const double (&brow)[N], double* q, double* r, double* tau, int tid) {
     constexpr int LD = N + 1;
-    for (int j = 0; j < N; ++j) q[tid + j * LD] = bm[tid + j * LD];
+#pragma unroll
+    for (int j = 0; j < N; ++j) q[tid + j * LD] = brow[j];
     __syncthreads();
     for (int i = 0; i < N; ++i) {
         // DLARFG on column i (every thread evaluates the same scalars)
@@ -280,8 +284,7 @@ coop_broyden_kernel(DevParams p, long long nsys, long long B, double* __restrict
     using S = CoopBroydenSmem<N>;
     constexpr int LD = S::LD;
     extern __shared__ double smem[];
-    double* bm = smem;
-    double* q = bm + S::MAT;
+    double* q = smem;
     double* r = q + S::MAT;
     double* x = r + S::MAT;
     double* fvec = x + N;
@@ -293,8 +296,10 @@ coop_broyden_kernel(DevParams p, long long nsys, long long B, double* __restrict
     double* w = s + N;
     double* cs = w + N;
     double* sn = cs + N;
-    double* tau = sn + N;
-    double* xp = tau + N;     // perturbed copy of x for the forward differences
+    double* stage = sn + N;   // STAGE x N staging rows for B^T f
+    double* tau = w;          // Householder scalars: only live inside the refactorisation
+    double* xp = s;           // perturbed copy of x for the forward differences: only live there too
+    double brow[N];           // row `tid` of the Broyden matrix B
     const int tid = threadIdx.x;
     const long long b = blockIdx.x;
     if (b >= nsys) return;
@@ -323,6 +328,7 @@ coop_broyden_kernel(DevParams p, long long nsys, long long B, double* __restrict
                 xp[tid] = x[tid];
                 __syncthreads();
                 const double eps = 0x1p-26;
+#pragma unroll
                 for (int j = 0; j < N; ++j) {
                     const double temp = x[j];
                     double h = eps * fabs(temp);
@@ -330,13 +336,13 @@ coop_broyden_kernel(DevParams p, long long nsys, long long B, double* __restrict
                     if (tid == 0) xp[j] = temp + h;
                     __syncthreads();
                     const double f1 = F::component(xp, tid, N, c);
-                    bm[tid + j * LD] = (f1 - fvec[tid]) / h;
+                    brow[j] = (f1 - fvec[tid]) / h;
                     __syncthreads();
                     if (tid == 0) xp[j] = temp;
                 }
                 ++njac;
                 __syncthreads();
-                cb_qr_full<N>(bm, q, r, tau, tid);
+                cb_qr_full<N>(brow, q, r, tau, tid);
                 jcount = 0;
             } else {
                 df[tid] = fvec[tid] - fvold[tid];
@@ -345,8 +351,8 @@ coop_broyden_kernel(DevParams p, long long nsys, long long B, double* __restrict
                 const double x2 = cb_dot<N>(dx, dx);
                 {   // s = df - matmul(b, dx): row t accumulates over j from zero
                     double acc = 0.0;
-#pragma unroll 8
-                    for (int j = 0; j < N; ++j) acc = acc + bm[tid + j * LD] * dx[j];
+#pragma unroll
+                    for (int j = 0; j < N; ++j) acc = acc + brow[j] * dx[j];
                     double sv = df[tid] - acc;
                     // recip_mult_array (DRSCL)
                     const double smlnum = 0x1p-1022, bignum = 1.0 / smlnum;
@@ -363,9 +369,10 @@ coop_broyden_kernel(DevParams p, long long nsys, long long B, double* __restrict
                     }
                     s[tid] = sv;
                     // rank1_update (DGER, alpha = 1): row t of B
+#pragma unroll
                     for (int j = 0; j < N; ++j) {
                         const double dj = dx[j];
-                        if (dj != 0.0) bm[tid + j * LD] = bm[tid + j * LD] + sv * (1.0 * dj);
+                        if (dj != 0.0) brow[j] = brow[j] + sv * (1.0 * dj);
                     }
                 }
                 __syncthreads();
@@ -376,10 +383,21 @@ coop_broyden_kernel(DevParams p, long long nsys, long long B, double* __restrict
             // gradient B^T F -> dx ; save state ; -Q^T F -> df
             {
                 double t1 = 0.0, t2 = 0.0;
-                const double* bc = bm + tid * LD;
+                // column `tid` of B^T f = sum_i b(i, tid) f(i) in the order i = 0, 1, ...: rows of B are published
+                // STAGE at a time from the registers of their owners, every thread then adds its column's terms
+                constexpr int ST = S::STAGE < N ? S::STAGE : N;
+                for (int i0 = 0; i0 < N; i0 += ST) {
+                    if (tid >= i0 && tid < i0 + ST) {
+                        double* dst = stage + (tid - i0) * N;
+#pragma unroll
+                        for (int j = 0; j < N; ++j) dst[j] = brow[j];
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int u = 0; u < ST; ++u) t1 += stage[u * N + tid] * fvec[i0 + u];
+                    __syncthreads();
+                }
                 const double* qc = q + tid * LD;
-#pragma unroll 8
-                for (int i = 0; i < N; ++i) t1 += bc[i] * fvec[i];
 #pragma unroll 8
                 for (int i = 0; i < N; ++i) t2 += qc[i] * fvec[i];
                 __syncthreads();          // everyone is done reading dx / df of the update step

@@ -120,16 +120,12 @@ DevParams to_dev(const nlb_params* p) {
 #define NLB_TPS_BLOCK 128
 #endif
 constexpr int TPS_BLOCK = NLB_TPS_BLOCK;
-// Minimum resident CTAs per SM asked of ptxas.  Measured on B200 (scripts/sweep_variants.py): capping the
-// 2x2 Broyden kernel at 80 registers (6 CTAs/SM) is 11 % faster than 110 registers (4 CTAs/SM); the LM and
-// Newton kernels do not gain from tighter caps.
+// Minimum resident CTAs per SM asked of ptxas.  Measured on B200 (launch-bounds sweep): capping the
+// 2x2 Broyden kernel at 80 registers (6 CTAs/SM) is 11 % faster than 110 registers (4 CTAs/SM); LM is best at
+// 3 CTAs/SM (160 registers); Newton does not gain from a cap.
 template <int SOLVER>
 constexpr int tps_min_blocks() {
-#ifdef NLB_TPS_MINB
-    return NLB_TPS_MINB;
-#else
     return SOLVER == 2 ? 6 : (SOLVER == 0 ? 3 : 1);
-#endif
 }
 
 template <class F, int SOLVER>

@@ -27,21 +27,6 @@ NLB_DEV double nl_sign(double a, double b) { return copysign(fabs(a), b); }
 // 235,291,299,313,346,475,501,511,531,554,612,642,660 and src/nonlin_linesearch.f90:569).
 struct Norm2 {
     double scale = 1.0, ssq = 0.0;
-#ifdef NLB_NORM2_BRANCHY
-    NLB_DEV void add(double x) {
-        if (x != 0.0) {
-            double a = fabs(x);
-            if (scale < a) {
-                double t = scale / a;
-                ssq = 1.0 + ssq * t * t;
-                scale = a;
-            } else {
-                double t = a / scale;
-                ssq += t * t;
-            }
-        }
-    }
-#else
     NLB_DEV void add(double x) {
         if (x != 0.0) {
             // one division serves both cases (scale/a when a new maximum arrives, a/scale otherwise);
@@ -54,23 +39,8 @@ struct Norm2 {
             scale = up ? a : scale;
         }
     }
-#endif
     NLB_DEV double value() const { return scale * sqrt(ssq); }
 };
-
-// NORM2 of a[i0*stride .. (i1-1)*stride] (per-thread array, run-time bounds): the loads are issued seven at
-// a time so their latency overlaps; the accumulation order is unchanged.
-NLB_DEV void norm2_range(Norm2& acc, const double* a, int i0, int i1) {
-    int i = i0;
-    for (; i + 7 <= i1; i += 7) {
-        double t[7];
-#pragma unroll
-        for (int u = 0; u < 7; ++u) t[u] = a[i + u];
-#pragma unroll
-        for (int u = 0; u < 7; ++u) acc.add(t[u]);
-    }
-    for (; i < i1; ++i) acc.add(a[i]);
-}
 
 // Short register vectors: the plain two-branch form of the same recurrence is slightly faster there
 // (measured on the 2x2 Broyden kernel), the select form wins in the long local-memory loops of LM.

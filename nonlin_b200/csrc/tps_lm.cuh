@@ -15,11 +15,9 @@
 
 namespace nlb {
 
-#ifndef NLB_UNROLL_M_FACTOR
-#define NLB_UNROLL_M_FACTOR 1   // measured on B200: 7 raises the 21x4 kernel to 206 registers and costs 30 %
-#endif
-constexpr int kUnrollM = NLB_UNROLL_M_FACTOR;   // unroll factor of the loops over the m equations of tall systems
-#define NLB_UNROLL_M _Pragma("unroll(M <= 8 ? M : kUnrollM)")
+// Loops over the m equations: fully unrolled for small systems (registers), rolled for tall ones (measured on
+// B200: unrolling the 21-row loops 7-fold raises the kernel to 206 registers and costs 30 %).
+#define NLB_UNROLL_M _Pragma("unroll(M <= 8 ? M : 1)")
 
 // Pivoted Householder QR in place (MINPACK QRFAC lineage).  ipvt is 0-based.
 template <int M, int N>

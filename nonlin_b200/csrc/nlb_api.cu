@@ -208,8 +208,11 @@ tps_jacobian_kernel(int analytic, long long B, const double* __restrict__ x, dou
 // ---------------------------------------------------------------------------------------
 // batch statistics
 // ---------------------------------------------------------------------------------------
-__global__ void stats_kernel(long long B, const nlb_iteration_behavior* __restrict__ ib,
-                             const int32_t* __restrict__ status, unsigned long long* __restrict__ out) {
+__global__ void __launch_bounds__(256)
+stats_kernel(long long B, const nlb_iteration_behavior* __restrict__ ib, const int32_t* __restrict__ status,
+             unsigned long long* __restrict__ out) {
+    // grid-stride accumulation in registers, warp shuffle, one shared-memory pass per block, then one atomic per
+    // block and statistic (HBM-bound: 32 B per system)
     unsigned long long v[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
         const int st = status ? status[b] : 0;
@@ -217,26 +220,36 @@ __global__ void stats_kernel(long long B, const nlb_iteration_behavior* __restri
         v[NLB_STAT_CONVERGED] += (st == 0);
         v[NLB_STAT_FAILED] += (st != 0);
         if (ib) {
-            const nlb_iteration_behavior o = ib[b];
-            v[NLB_STAT_CONVERGED_FCN] += (o.converge_on_fcn != 0);
-            v[NLB_STAT_CONVERGED_CHNG] += (o.converge_on_chng != 0);
-            v[NLB_STAT_CONVERGED_ZERO_DIFF] += (o.converge_on_zero_diff != 0);
-            v[NLB_STAT_SUM_ITER] += (unsigned long long)o.iter_count;
-            v[NLB_STAT_SUM_FCN] += (unsigned long long)o.fcn_count;
-            v[NLB_STAT_SUM_JAC] += (unsigned long long)o.jacobian_count;
-            v[NLB_STAT_MAX_ITER] = max(v[NLB_STAT_MAX_ITER], (unsigned long long)o.iter_count);
+            const int* r = reinterpret_cast<const int*>(ib + b);
+            const int it = r[0], nf = r[1], nj = r[2], cf = r[4], cx = r[5], cg = r[6];
+            v[NLB_STAT_CONVERGED_FCN] += (cf != 0);
+            v[NLB_STAT_CONVERGED_CHNG] += (cx != 0);
+            v[NLB_STAT_CONVERGED_ZERO_DIFF] += (cg != 0);
+            v[NLB_STAT_SUM_ITER] += (unsigned long long)it;
+            v[NLB_STAT_SUM_FCN] += (unsigned long long)nf;
+            v[NLB_STAT_SUM_JAC] += (unsigned long long)nj;
+            v[NLB_STAT_MAX_ITER] = max(v[NLB_STAT_MAX_ITER], (unsigned long long)it);
         }
     }
+    __shared__ unsigned long long part[8][10];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < 10; ++k) {
         unsigned long long s = v[k];
         if (k == NLB_STAT_MAX_ITER) {
             for (int off = 16; off > 0; off >>= 1) s = max(s, __shfl_down_sync(0xffffffffu, s, off));
-            if ((threadIdx.x & 31) == 0) atomicMax(&out[k], s);
         } else {
             for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
-            if ((threadIdx.x & 31) == 0 && s) atomicAdd(&out[k], s);
         }
+        if (lane == 0) part[warp][k] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 10) {
+        const int k = threadIdx.x;
+        unsigned long long s = part[0][k];
+        for (int w = 1; w < 8; ++w) s = (k == NLB_STAT_MAX_ITER) ? max(s, part[w][k]) : s + part[w][k];
+        if (k == NLB_STAT_MAX_ITER) atomicMax(&out[k], s);
+        else if (s) atomicAdd(&out[k], s);
     }
 }
 
@@ -647,7 +660,8 @@ int nlb_reduce_stats(nlb_handle* h, int64_t B, const nlb_iteration_behavior* ib,
     NLB_CUDA(h, cudaMemsetAsync(d, 0, sizeof(int64_t) * NLB_STAT_COUNT, s));
     if (B > 0) {
         unsigned grid = (unsigned)((B + 255) / 256);
-        if (grid > 148u * 8u) grid = 148u * 8u;
+        const unsigned cap = (unsigned)(h->num_sms > 0 ? h->num_sms : 148) * 4u;   // persistent-style: 4 CTAs per SM
+        if (grid > cap) grid = cap;
         stats_kernel<<<grid, 256, 0, s>>>(B, (const nlb_iteration_behavior*)aib.dev, (const int32_t*)ast.dev,
                                           (unsigned long long*)d);
         ++h->launches;

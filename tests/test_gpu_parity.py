@@ -508,3 +508,26 @@ def test_custom_line_search_object(engine, oracle):
         assert np.array_equal(st, sto) and np.array_equal(x, xo) and np.array_equal(f, fo) and np.array_equal(ib, ibo)
         if max_ev == 2:
             assert (st == nb.NL_CONVERGENCE_ERROR).any()
+
+
+@pytest.mark.parametrize("solver,fcn,m,n", [("quasi_newton", "misc_2fcn", 2, 2), ("newton", "powell_badly_scaled", 2, 2),
+                                             ("least_squares", "lsq_poly_fit", 21, 4), ("least_squares", "misc_2fcn", 2, 2)])
+def test_non_finite_and_degenerate_starts_terminate_like_the_oracle(engine, oracle, solver, fcn, m, n):
+    """NaN / Inf / huge / zero starting points: no hang, and the same per-system outcome as the oracle
+    (the reference would `error stop` or return garbage; the engine must at least agree and terminate)."""
+    import nonlin_b200 as nb
+
+    vals = [np.nan, np.inf, -np.inf, 0.0, 1e308, -1e308, 1e-320, 1.0]
+    B = len(vals) * 2
+    x0 = np.ones((n, B))
+    for i, v in enumerate(vals):
+        x0[0, 2 * i] = v
+        x0[n - 1, 2 * i + 1] = v
+    rng = np.random.default_rng(3)
+    args = rng.standard_normal((21, B)) if fcn == "lsq_poly_fit" else None
+    w = dict(solver=solver, fcn=fcn, m=m, n=n, x0=x0, args=args, shared=None, settings={})
+    with np.errstate(all="ignore"):
+        x, f, ib, st = run_engine(nb, w)
+        xo, fo, ibo, sto = oracle.solve_batch(solver, fcn, x0, m=m, sys=args)
+    assert np.array_equal(st, sto) and np.array_equal(ib, ibo)
+    assert np.array_equal(x, xo, equal_nan=True) and np.array_equal(f, fo, equal_nan=True)

@@ -3,12 +3,14 @@
 
 #include "coop_broyden.cuh"
 #include "coop_lm.cuh"
+#include "coop_lm_cta.cuh"
 
 namespace nlb {
 
 namespace {
 
 enum { SOLVER_LM = 0, SOLVER_NEWTON = 1, SOLVER_BROYDEN = 2 };
+constexpr int WLM_MIN_M = 512;   // rows from which the CTA-per-system LM kernel is used
 
 template <class F, int N>
 int launch_broyden(const DevParams& p, long long nsys, long long B, double* x, double* fvec, const double* sys, const double* shared,
@@ -136,14 +138,49 @@ int launch_lm(const DevParams& p, long long ntot, long long B, int m, double* x,
     return NLB_OK;
 }
 
+// Tall systems: CTA-per-system / warp-per-column kernel (coop_lm_cta.cuh), persistent CTAs + work queue.
+template <class F, int N>
+int launch_wlm(const DevParams& p, long long ntot, long long B, int m, double* x, double* fvec, const double* sys,
+               const double* shared, nlb_iteration_behavior* ib, int32_t* status, cudaStream_t s, int64_t* launches) {
+    using S = WlmSmem<N>;
+    static int ctas_per_sm = 0, num_sms = 0;
+    if (ctas_per_sm == 0) {
+        int dev = 0;
+        if (cudaFuncSetAttribute(wlm_kernel<F, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES) != cudaSuccess ||
+            cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, wlm_kernel<F, N>, 32 * N, S::BYTES) != cudaSuccess)
+            return NLB_ERR_CUDA;
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
+    long long grid = ntot;
+    if (grid > (long long)num_sms * ctas_per_sm) grid = (long long)num_sms * ctas_per_sm;
+    const size_t per_cta = (size_t)(N + 3) * (size_t)m;          // doubles
+    double* ws = nullptr;
+    if (cudaMallocAsync((void**)&ws, (per_cta * (size_t)grid + 8) * sizeof(double), s) != cudaSuccess) return NLB_ERR_CUDA;
+    unsigned long long* cursor = reinterpret_cast<unsigned long long*>(ws + per_cta * (size_t)grid);
+    if (cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), s) != cudaSuccess) { cudaFreeAsync(ws, s); return NLB_ERR_CUDA; }
+    wlm_kernel<F, N><<<(unsigned)grid, 32 * N, S::BYTES, s>>>(p, B, ntot, m, x, fvec, sys, shared, ib, status, ws, cursor);
+    ++*launches;
+    if (cudaGetLastError() != cudaSuccess) { cudaFreeAsync(ws, s); return NLB_ERR_CUDA; }
+    if (cudaFreeAsync(ws, s) != cudaSuccess) return NLB_ERR_CUDA;
+    return NLB_OK;
+}
+
 }  // namespace
 
 int launch_coop_lm(int fcn_id, const DevParams& p, long long nsys, long long B, int m, int n, double* x, double* fvec, const double* sys,
                    const double* shared, nlb_iteration_behavior* ib, int32_t* status, cudaStream_t s, int64_t* launches) {
     if (m < n) return NLB_ERR_UNSUPPORTED;
     switch (fcn_id) {
-        case FCN_RATIONAL_7_8: return launch_lm<Rational78, 16>(p, nsys, B, m, x, fvec, sys, shared, ib, status, s, launches);
-        case FCN_EXP_SUM_8: return launch_lm<ExpSum8, 16>(p, nsys, B, m, x, fvec, sys, shared, ib, status, s, launches);
+        // tall fits: one CTA per system (a lone slow system costs ~1 ms per iteration instead of ~17 ms);
+        // short ones: one lane per system (more systems in flight)
+        case FCN_RATIONAL_7_8:
+            if (m >= WLM_MIN_M) return launch_wlm<Rational78, 16>(p, nsys, B, m, x, fvec, sys, shared, ib, status, s, launches);
+            return launch_lm<Rational78, 16>(p, nsys, B, m, x, fvec, sys, shared, ib, status, s, launches);
+        case FCN_EXP_SUM_8:
+            if (m >= WLM_MIN_M) return launch_wlm<ExpSum8, 16>(p, nsys, B, m, x, fvec, sys, shared, ib, status, s, launches);
+            return launch_lm<ExpSum8, 16>(p, nsys, B, m, x, fvec, sys, shared, ib, status, s, launches);
         case FCN_EXP_DECAY_4: return launch_lm<ExpDecay4, 4>(p, nsys, B, m, x, fvec, sys, shared, ib, status, s, launches);
         default: return NLB_ERR_UNSUPPORTED;
     }

@@ -46,22 +46,28 @@ NLB_DEV void clm_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0]
 constexpr int CLM_PF = 48;   // rows ahead
 
 // per-lane views into [element][32] shared arrays
-struct LaneVec {
+template <int S>
+struct SVec {
     double* p;
-    NLB_DEV double& operator[](int i) const { return p[i * 32]; }
+    NLB_DEV double& operator[](int i) const { return p[i * S]; }
 };
-template <int N>
-struct LaneMat {
+template <int N, int S>
+struct SMat {
     double* p;
-    NLB_DEV double& operator()(int i, int j) const { return p[(i + j * N) * 32]; }
+    NLB_DEV double& operator()(int i, int j) const { return p[(i + j * N) * S]; }
 };
-struct LaneIVec {
+template <int S>
+struct SIVec {
     int* p;
-    NLB_DEV int& operator[](int i) const { return p[i * 32]; }
+    NLB_DEV int& operator[](int i) const { return p[i * S]; }
 };
-
+using LaneVec = SVec<32>;          // [element][lane] arrays of the lane-per-system kernel
 template <int N>
-NLB_DEV double clm_norm2(const LaneVec& v) {
+using LaneMat = SMat<N, 32>;
+using LaneIVec = SIVec<32>;
+
+template <int N, class V>
+NLB_DEV double clm_norm2(const V& v) {
     Norm2 acc;
     for (int i = 0; i < N; ++i) acc.add(v[i]);
     return acc.value();
@@ -181,9 +187,9 @@ NLB_DEV double clm_coop_norm2(bool on, const double* __restrict__ v, long long s
 }
 
 // lmsolve on the n x n block held in shared memory (strict lower triangle = scratch for S^T).
-template <int N>
-NLB_DEV void clm_qrsolve(const LaneMat<N>& r, const LaneIVec& ipvt, const LaneVec& diag, const LaneVec& qtb,
-                         const LaneVec& x, const LaneVec& sdiag, const LaneVec& wa) {
+template <int N, class Mt, class IV, class V>
+NLB_DEV void clm_qrsolve(const Mt& r, const IV& ipvt, const V& diag, const V& qtb, const V& x, const V& sdiag,
+                         const V& wa) {
     for (int j = 0; j < N; ++j) {
         for (int i = j; i < N; ++i) r(i, j) = r(j, i);
         x[j] = r(j, j);
@@ -241,10 +247,10 @@ NLB_DEV void clm_qrsolve(const LaneMat<N>& r, const LaneIVec& ipvt, const LaneVe
 // lmpar.  wa2 is the reference's m-element work array: its first n entries are w4h (shared
 // memory), entries n..m-1 are the tail of the HBM vector w4 (stride 32) — the in-loop dxnorm
 // runs over all m of them (src/nonlin_least_squares.f90:531).
-template <int N>
-NLB_DEV void clm_par(const LaneMat<N>& r, const LaneIVec& ipvt, const LaneVec& diag, const LaneVec& qtb, double delta,
-                     double& par, const LaneVec& x, const LaneVec& sdiag, const LaneVec& wa1, const LaneVec& w4h,
-                     const double* __restrict__ w4, int m) {
+// `tail(scale, ssq)` continues the NORM2 recurrence over entries n..m-1 of the work array (how depends on the kernel).
+template <int N, class Mt, class IV, class V, class Tail>
+NLB_DEV void clm_par(const Mt& r, const IV& ipvt, const V& diag, const V& qtb, double delta, double& par, const V& x,
+                     const V& sdiag, const V& wa1, const V& w4h, Tail tail) {
     const double dwarf = 0x1p-1022;
     int nsing = N;
     for (int j = 0; j < N; ++j) {
@@ -303,7 +309,7 @@ NLB_DEV void clm_par(const LaneMat<N>& r, const LaneIVec& ipvt, const LaneVec& d
         {
             Norm2 acc;
             for (int i = 0; i < N; ++i) acc.add(w4h[i]);
-            clm_norm2_strided(acc, w4, 32, N, m);
+            tail(acc.scale, acc.ssq);
             dxnorm = acc.value();
         }
         temp = fp;
@@ -696,7 +702,12 @@ coop_lm_kernel(DevParams p, long long B, long long b0, long long nsys, int m, do
             if (state == CLM_INNER) {
                 double par = sc[SC_PAR];
                 double delta = sc[SC_DELTA];
-                clm_par<N>(R, ipvt, diag, qtf, delta, par, wa1, wa2, wa3, w4h, w4, m);
+                clm_par<N>(R, ipvt, diag, qtf, delta, par, wa1, wa2, wa3, w4h, [&](double& scale, double& ssq) {
+                    Norm2 acc;
+                    acc.scale = scale; acc.ssq = ssq;
+                    clm_norm2_strided(acc, w4, 32, N, m);
+                    scale = acc.scale; ssq = acc.ssq;
+                });
                 for (int j = 0; j < N; ++j) {
                     const double pj = -wa1[j];
                     wa1[j] = pj;

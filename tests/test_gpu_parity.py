@@ -396,7 +396,8 @@ def test_runtime_family_eval(engine, oracle):
             assert np.array_equal(f[:, b], fo)
 
 
-@pytest.mark.parametrize("name,B,kw", [("LM4", 200, {"m": 64}), ("LM4", 70, {"m": 33}), ("C4", 40, {"m": 64}), ("C4", 33, {"m": 256})])
+@pytest.mark.parametrize("name,B,kw", [("LM4", 200, {"m": 64}), ("LM4", 70, {"m": 33}), ("C4", 40, {"m": 64}), ("C4", 33, {"m": 256}),
+                                        ("C4", 200, {"m": 640}), ("C4", 37, {"m": 1531})])   # m >= 512: CTA-per-system kernel
 def test_tall_lm_parity(engine, oracle, name, B, kw):
     """Curve-fit LM with run-time m (BASELINE config 4 family and the 4-parameter fits): thread per
     (system, column), Jacobian in HBM, every m-length sum walked in the reference's order -> bitwise."""

@@ -33,7 +33,8 @@ constexpr int WLM_SEG = 256;   // rows per staged segment of a warp
 
 template <int N>
 struct WlmSmem {
-    static constexpr int NDV = 7 * N + N * N + 16 + N * WLM_SEG;
+    static constexpr int NGRP = N * WLM_SEG / 32;     // 32-row groups the CTA staging buffer can hold
+    static constexpr int NDV = 7 * N + N * N + 16 + N * WLM_SEG + NGRP;
     static constexpr int NIV = 2 * N + 16;
     static constexpr size_t BYTES = (size_t)NDV * sizeof(double) + (size_t)NIV * sizeof(int) + 16;
 };
@@ -117,12 +118,104 @@ NLB_DEV void wlm_norm2(double& scale, double& ssq, int i0, int i1, double* stage
     ssq = __shfl_sync(0xffffffffu, ssq, 0);
 }
 
+
+// NORM2 of load(i), i in [i0, i1), by the whole CTA (all threads must call; result valid in thread 0 after the
+// last barrier inside).  Same recurrence, same order as libgfortran:
+//   1. 32-row groups are dealt round-robin to the warps; each finds its group's max|x| (coalesced load + reduce)
+//   2. an exclusive prefix maximum over the groups gives the running scale entering each group; inside a group a warp
+//      max-scan gives it per element; the lanes then form the quotients (all divisions, in parallel) and store
+//      t*t for ordinary elements, -t for an element that raises the scale, into the CTA's staging buffer
+//   3. thread 0 replays ssq in index order: a plain add chain, with the rare scale-raising element handled apart
+// Requires i1 - i0 <= N * WLM_SEG (the staging buffer); gmax: (N * WLM_SEG / 32) doubles of shared memory.
+template <int N, class L>
+NLB_DEV double wlm_cta_norm2(int i0, int i1, double* qbuf, double* gmax, int tid, L load) {
+    const int lane = tid & 31, w = tid >> 5;
+    const int L_ = i1 - i0;
+    const int ngroups = (L_ + 31) / 32;
+    for (int g = w; g < ngroups; g += N) {
+        const int i = i0 + g * 32 + lane;
+        const double a = (i < i1) ? fabs(load(i)) : 0.0;
+        double pm = (a == a) ? a : 0.0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const double t = __shfl_xor_sync(0xffffffffu, pm, d);
+            if (t > pm) pm = t;
+        }
+        if (lane == 0) gmax[g] = pm;
+    }
+    __syncthreads();
+    for (int g = w; g < ngroups; g += N) {
+        // running scale entering group g: max(1, maxima of the groups before it)
+        double sc0 = 1.0;
+        for (int h = lane; h < g; h += 32) { const double t = gmax[h]; if (t > sc0) sc0 = t; }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const double t = __shfl_xor_sync(0xffffffffu, sc0, d);
+            if (t > sc0) sc0 = t;
+        }
+        const int i = i0 + g * 32 + lane;
+        const bool valid = i < i1;
+        const double x = valid ? load(i) : 0.0;
+        const double a = fabs(x);
+        double pm = (a == a) ? a : 0.0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, pm, d);
+            if (lane >= d && t > pm) pm = t;
+        }
+        double excl = __shfl_up_sync(0xffffffffu, pm, 1);
+        if (lane == 0) excl = 0.0;
+        const double sc = (sc0 < excl) ? excl : sc0;
+        double q = 0.0;
+        if (valid && x != 0.0) {
+            const bool up = sc < a;
+            const double t = (up ? sc : a) / (up ? a : sc);
+            q = up ? -fmax(t, 4.9406564584124654e-324) : t * t;
+        }
+        if (valid) qbuf[g * 32 + lane] = q;
+    }
+    __syncthreads();
+    double result = 0.0;
+    if (tid == 0) {
+        double scale = 1.0;
+        for (int g = 0; g < ngroups; ++g) { const double t = gmax[g]; if (t > scale) scale = t; }
+        double ssq = 0.0;
+        int t = 0;
+        for (; t + 8 <= L_; t += 8) {
+            double q[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) q[u] = qbuf[t + u];
+            double mn = q[0];
+#pragma unroll
+            for (int u = 1; u < 8; ++u) mn = fmin(mn, q[u]);
+            if (mn >= 0.0) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) ssq = ssq + q[u];
+            } else {
+#pragma unroll 1
+                for (int u = 0; u < 8; ++u) {
+                    if (q[u] < 0.0) { const double tt = -q[u]; ssq = 1.0 + ssq * tt * tt; }
+                    else ssq = ssq + q[u];
+                }
+            }
+        }
+        for (; t < L_; ++t) {
+            const double q = qbuf[t];
+            if (q < 0.0) { const double tt = -q; ssq = 1.0 + ssq * tt * tt; }
+            else ssq = ssq + q;
+        }
+        result = scale * sqrt(ssq);
+    }
+    __syncthreads();
+    return result;
+}
+
 enum { WS_FNORM = 0, WS_PAR, WS_XNORM, WS_DELTA, WS_GNORM, WS_AJNORM, WS_AJJ, WS_PNORM, WS_TEMP, WS_F1 };
 enum { WI_ITER = 0, WI_NEVAL, WI_NJAC, WI_FLAG, WI_FCN, WI_XCN, WI_GCN, WI_PIVOT, WI_ACCEPT, WI_NEXT };
 enum { WN_INNER = 0, WN_OUTER = 1, WN_DONE = 2 };
 
 template <class F, int N>
-__global__ void __launch_bounds__(32 * N)
+__global__ void __launch_bounds__(32 * N, 2)
 wlm_kernel(DevParams p, long long B, long long nsys, int m, double* __restrict__ xg, double* __restrict__ fg,
            const double* __restrict__ sys, const double* __restrict__ shared, nlb_iteration_behavior* __restrict__ ibg,
            int32_t* __restrict__ statusg, double* __restrict__ ws, unsigned long long* __restrict__ cursor) {
@@ -136,7 +229,8 @@ wlm_kernel(DevParams p, long long B, long long nsys, int m, double* __restrict__
         w4h{smem + 6 * N}, sc{smem + 7 * N + N * N};
     const Mt R{smem + 7 * N};
     double* stage_all = smem + 7 * N + N * N + 16;
-    int* ibase = reinterpret_cast<int*>(stage_all + N * WLM_SEG);
+    double* gmax = stage_all + N * WLM_SEG;
+    int* ibase = reinterpret_cast<int*>(gmax + WlmSmem<N>::NGRP);
     const IV ipvt{ibase}, pos{ibase + N}, si{ibase + 2 * N};
     unsigned long long* cur_s = reinterpret_cast<unsigned long long*>(ibase + 2 * N + 16);
 
@@ -177,7 +271,11 @@ wlm_kernel(DevParams p, long long B, long long nsys, int m, double* __restrict__
             for (int i = tid; i < m; i += T) fv[i] = F::residual(xl, __ldg(shared + i), yv[i]);
         }
         __syncthreads();
-        if (w == 0) {
+        const bool fits = m <= N * WLM_SEG;       // the CTA staging buffer holds a whole m-vector of quotients
+        if (fits) {
+            const double fn = wlm_cta_norm2<N>(0, m, stage_all, gmax, tid, [&](int i) { return fv[i]; });
+            if (tid == 0) sc[WS_FNORM] = fn;
+        } else if (w == 0) {
             double scale = 1.0, ssq = 0.0;
             wlm_norm2(scale, ssq, 0, m, stage, lane, [&](int i) { return fv[i]; });
             if (lane == 0) sc[WS_FNORM] = scale * sqrt(ssq);
@@ -229,7 +327,13 @@ wlm_kernel(DevParams p, long long B, long long nsys, int m, double* __restrict__
                 __syncthreads();
                 const int pc = si[WI_PIVOT];
                 const double* Jp = J + (size_t)pc * m;
-                if (w == pc) {
+                if (fits) {
+                    double ajnorm = wlm_cta_norm2<N>(j, m, stage_all, gmax, tid, [&](int i) { return Jp[i]; });
+                    if (tid == 0) {
+                        if (ajnorm != 0.0 && Jp[j] < 0.0) ajnorm = -ajnorm;
+                        sc[WS_AJNORM] = ajnorm;
+                    }
+                } else if (w == pc) {
                     double scale = 1.0, ssq = 0.0;
                     wlm_norm2(scale, ssq, j, m, stage, lane, [&](int i) { return Jw[i]; });
                     if (lane == 0) {
@@ -381,7 +485,10 @@ wlm_kernel(DevParams p, long long B, long long nsys, int m, double* __restrict__
                     for (int i = tid; i < m; i += T) w4[i] = F::residual(xl, __ldg(shared + i), yv[i]);
                 }
                 __syncthreads();
-                if (w == 0) {
+                if (fits) {
+                    const double f1n = wlm_cta_norm2<N>(0, m, stage_all, gmax, tid, [&](int i) { return w4[i]; });
+                    if (tid == 0) sc[WS_F1] = f1n;
+                } else if (w == 0) {
                     double scale = 1.0, ssq = 0.0;
                     wlm_norm2(scale, ssq, 0, m, stage, lane, [&](int i) { return w4[i]; });
                     if (lane == 0) sc[WS_F1] = scale * sqrt(ssq);

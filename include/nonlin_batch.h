@@ -163,6 +163,11 @@ int nlb_reduce_stats(nlb_handle* handle, int64_t B, const nlb_iteration_behavior
  * second number. */
 int nlb_measure_fp64_peak(nlb_handle* handle, double* dfma_tflops, double* dadd_dmul_tflops);
 
+/* Dependent-chain latencies on this GPU, in SM cycles per operation: cycles4[0] = DADD, [1] = IEEE division,
+ * [2] = sqrt (+ one add), [3] = shared-memory load + DADD.  These bound the serial chains (ordered sums, Givens
+ * chains, triangular solves) that the reference's summation order imposes. */
+int nlb_measure_fp64_latency(nlb_handle* handle, double* cycles4);
+
 #ifdef __cplusplus
 }
 #endif

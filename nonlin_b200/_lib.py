@@ -40,6 +40,7 @@ EXPORTS = [
     "nlb_vecfcn_count", "nlb_vecfcn_lookup", "nlb_vecfcn_name", "nlb_vecfcn_info",
     "nlb_least_squares_solve_batch", "nlb_newton_solve_batch", "nlb_quasi_newton_solve_batch",
     "nlb_vecfcn_eval_batch", "nlb_jacobian_batch", "nlb_reduce_stats", "nlb_measure_fp64_peak",
+    "nlb_measure_fp64_latency",
 ]
 
 
@@ -101,4 +102,5 @@ def load():
     lib.nlb_jacobian_batch.argtypes = [vp, C.POINTER(nlb_params), i32, i64, i32, i32, vp, vp, vp, vp, vp]
     lib.nlb_reduce_stats.argtypes = [vp, i64, vp, vp, vp, vp]
     lib.nlb_measure_fp64_peak.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl)]
+    lib.nlb_measure_fp64_latency.argtypes = [vp, C.POINTER(dbl)]
     return lib

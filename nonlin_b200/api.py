@@ -75,6 +75,12 @@ class Engine:
         self.check(_LIB.nlb_measure_fp64_peak(self._h, C.byref(a), C.byref(b)))
         return {"dfma_tflops": a.value, "dadd_dmul_tflops": b.value}
 
+    def measure_fp64_latency(self):
+        """Cycles per dependent DADD / division / sqrt / shared-load+DADD (the serial-chain floors)."""
+        v = (C.c_double * 4)()
+        self.check(_LIB.nlb_measure_fp64_latency(self._h, v))
+        return dict(zip(["dadd", "ddiv", "dsqrt", "lds_dadd"], [float(x) for x in v]))
+
     def reduce_stats(self, ib, status, B=None):
         """Batch convergence statistics -> dict (host)."""
         out = np.zeros(NLB_STAT_COUNT, dtype=np.int64)

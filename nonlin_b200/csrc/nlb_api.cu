@@ -275,6 +275,34 @@ __global__ void fp64_peak_kernel(double* out, int iters, double seed) {
     if (s == 12345.6789) out[0] = s;   // never true; keeps the chains alive
 }
 
+// Dependent-chain latencies of the FP64 operations the serial parts of the solvers are made of (one thread,
+// clock64 around a chain): cycles per dependent DADD, per dependent IEEE division, per dependent sqrt, and per
+// dependent shared-memory load + DADD (the replay loops of the cooperative kernels).
+__global__ void fp64_latency_kernel(double* out, int n, double seed) {
+    __shared__ double buf[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) buf[i] = 1e-9 * (i + 1);
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    double a = seed;
+    long long t0 = clock64();
+    for (int i = 0; i < n; ++i) a = __dadd_rn(a, 1e-9);
+    long long t1 = clock64();
+    double b = a;
+    for (int i = 0; i < n; ++i) b = b / 1.0000001;
+    long long t2 = clock64();
+    double c = b;
+    for (int i = 0; i < n; ++i) c = sqrt(c + 2.0);
+    long long t3 = clock64();
+    double d = c;
+    for (int i = 0; i < n; ++i) d = __dadd_rn(d, buf[i & 255]);
+    long long t4 = clock64();
+    out[0] = (double)(t1 - t0) / n;
+    out[1] = (double)(t2 - t1) / n;
+    out[2] = (double)(t3 - t2) / n;
+    out[3] = (double)(t4 - t3) / n;
+    out[4] = d;
+}
+
 // ---------------------------------------------------------------------------------------
 // dispatch
 // ---------------------------------------------------------------------------------------
@@ -671,6 +699,25 @@ int nlb_reduce_stats(nlb_handle* h, int64_t B, const nlb_iteration_behavior* ib,
         NLB_CUDA(h, cudaMemcpyAsync(stats, d, sizeof(int64_t) * NLB_STAT_COUNT, cudaMemcpyDeviceToHost, s));
         NLB_CUDA(h, cudaStreamSynchronize(s));
     }
+    return NLB_OK;
+}
+
+int nlb_measure_fp64_latency(nlb_handle* h, double* cycles4) {
+    if (!h || !cycles4) return NLB_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(h->mu);
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    double* dout = nullptr;
+    NLB_CUDA(h, cudaMalloc(&dout, 8 * sizeof(double)));
+    for (int rep = 0; rep < 2; ++rep) {
+        fp64_latency_kernel<<<1, 32, 0, h->stream>>>(dout, 20000, 1.0);
+        ++h->launches;
+    }
+    double host[8];
+    NLB_CUDA(h, cudaMemcpyAsync(host, dout, 5 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    NLB_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(dout);
+    for (int i = 0; i < 4; ++i) cycles4[i] = host[i];
     return NLB_OK;
 }
 

@@ -150,8 +150,10 @@ NLB_DEV double nl_exp(double x) {
     }
     const double t = r * r;
     const double c = r - t * (P1 + t * (P2 + t * (P3 + t * (P4 + t * P5))));
-    if (k == 0) return 1.0 - ((r * c) / (c - 2.0) - r);
-    double y = 1.0 - ((lo - (r * c) / (2.0 - c)) - hi);
+    // one division for both forms: (r*c)/(c-2) == -((r*c)/(2-c)) exactly (negation commutes with IEEE - and /)
+    const double q = (r * c) / (2.0 - c);
+    if (k == 0) return 1.0 - (-q - r);
+    double y = 1.0 - ((lo - q) - hi);
     if (k >= -1021) {
         if (k == 1024) return y * 2.0 * 8.98846567431158e+307;
         return __longlong_as_double(__double_as_longlong(y) + ((long long)k << 52));

@@ -122,13 +122,15 @@ NLB_DEV void tps_newton_refill(const DevParams& p, long long nsys, long long B, 
     int neval = 0, iter = 0, njac = 0, status = NLB_NO_ERROR;
     bool xcnvrg = false, fcnvrg = false, gcnvrg = false;
     long long b = -1;
-    bool active = false;
+    bool active = false, more = true;      // more: the queue may still hold systems for this lane
 
     for (;;) {
         bool finished = false;
-        if (!active) {
+        if (!active && more) {
             b = tps_fetch(cursor);
-            if (b >= nsys) break;
+            if (b >= nsys) more = false;
+        }
+        if (!active && more) {
 #pragma unroll
             for (int j = 0; j < N; ++j) x[j] = xg[j * B + b];
             const SysCtx c{sys ? sys + b : nullptr, shared, B, N, N};
@@ -143,6 +145,10 @@ NLB_DEV void tps_newton_refill(const DevParams& p, long long nsys, long long B, 
             if (test < ftol) { fcnvrg = true; finished = true; }
             else { stpmax = 100.0 * nl_max(norm2_vec(x), (double)N); active = true; }
         }
+        // No lane leaves the loop on its own: the warp re-converges here every trip (lanes that refilled and lanes
+        // that did not would otherwise run the iteration body as two half-empty groups) and exits together.
+        __syncwarp();
+        if (!__any_sync(0xffffffffu, active || finished || more)) break;
         if (active) {
             const SysCtx c{sys ? sys + b : nullptr, shared, B, N, N};
             ++iter;

@@ -142,6 +142,32 @@ int nlb_quasi_newton_solve_batch(nlb_handle* handle, const nlb_params* params, i
                                  double* x, double* fvec, const double* sys, const double* shared,
                                  nlb_iteration_behavior* ib, int32_t* status, void* stream);
 
+/* constrained_least_squares_solver: its own settings and the limits of constrained_equation_solver.
+ *   trust_region_radius   set_trust_region_radius  (cls_set_radius, src/nonlin_least_squares.f90:898-910; default 1, :64)
+ *   step_scaling_factor   set_step_scaling_factor  (cls_set_factor, :923-935; default 1, :66)
+ *   lower / upper         set_lower_limits / set_upper_limits (:812-855): n doubles each in HOST memory, shared by
+ *                         every system of the batch as they are shared by every solve of one solver object;
+ *                         NULL = the -huge / +huge arrays cls_solve installs when none were set (:1014-1024).
+ * As in the setters, a non-positive radius or factor selects 1. */
+typedef struct nlb_constrained_options {
+    double trust_region_radius;
+    double step_scaling_factor;
+    const double* lower;
+    const double* upper;
+} nlb_constrained_options;
+void nlb_constrained_options_default(nlb_constrained_options* o);
+
+/* constrained_least_squares_solver%solve  (cls_solve, src/nonlin_least_squares.f90:938-1176; dogleg :1301-1403,
+ * coleman_li_scaling :1222-1260, alpha_box :1181-1219, ces_apply_limits :858-883) over B systems.  Arguments as
+ * nlb_least_squares_solve_batch.  Available for the fixed-size residuals (m, n reported non-zero by
+ * nlb_vecfcn_info, n <= 8); others return NLB_ERR_UNSUPPORTED.  status[b] = 0 or NLB_CONVERGENCE_ERROR (:1173-1175);
+ * a system whose start (after clamping to the limits) or first residual is NaN or +-huge returns status 0 with an
+ * all-zero iteration_behavior, as the reference's early `return` does (:1043-1045). */
+int nlb_constrained_least_squares_solve_batch(nlb_handle* handle, const nlb_params* params,
+                                              const nlb_constrained_options* options, int fcn_id, int64_t B, int m,
+                                              int n, double* x, double* fvec, const double* sys, const double* shared,
+                                              nlb_iteration_behavior* ib, int32_t* status, void* stream);
+
 /* vecfcn_helper%fcn  (vfh_fcn, src/nonlin_multi_eqn_mult_var.f90:178-195) over B points. */
 int nlb_vecfcn_eval_batch(nlb_handle* handle, int fcn_id, int64_t B, int m, int n, const double* x, double* fvec,
                           const double* sys, const double* shared, void* stream);

@@ -25,6 +25,8 @@ from ._lib import (  # noqa: F401
 from .api import (  # noqa: F401
     Engine,
     NonlinError,
+    constrained_equation_solver,
+    constrained_least_squares_solver,
     default_engine,
     equation_solver,
     ib_view,

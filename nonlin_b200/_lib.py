@@ -40,7 +40,7 @@ EXPORTS = [
     "nlb_vecfcn_count", "nlb_vecfcn_lookup", "nlb_vecfcn_name", "nlb_vecfcn_info",
     "nlb_least_squares_solve_batch", "nlb_newton_solve_batch", "nlb_quasi_newton_solve_batch",
     "nlb_vecfcn_eval_batch", "nlb_jacobian_batch", "nlb_reduce_stats", "nlb_measure_fp64_peak",
-    "nlb_measure_fp64_latency",
+    "nlb_measure_fp64_latency", "nlb_constrained_options_default", "nlb_constrained_least_squares_solve_batch",
 ]
 
 
@@ -58,6 +58,15 @@ class nlb_params(C.Structure):
         ("ls_factor", C.c_double),
         ("use_analytic_jacobian", C.c_int32),
         ("max_iter_guard", C.c_int32),
+    ]
+
+
+class nlb_constrained_options(C.Structure):
+    _fields_ = [
+        ("trust_region_radius", C.c_double),
+        ("step_scaling_factor", C.c_double),
+        ("lower", C.c_void_p),
+        ("upper", C.c_void_p),
     ]
 
 
@@ -98,6 +107,10 @@ def load():
     solve_args = [vp, C.POINTER(nlb_params), i32, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     for name in ("nlb_least_squares_solve_batch", "nlb_newton_solve_batch", "nlb_quasi_newton_solve_batch"):
         getattr(lib, name).argtypes = solve_args
+    lib.nlb_constrained_options_default.argtypes = [C.POINTER(nlb_constrained_options)]
+    lib.nlb_constrained_options_default.restype = None
+    lib.nlb_constrained_least_squares_solve_batch.argtypes = (
+        [vp, C.POINTER(nlb_params), C.POINTER(nlb_constrained_options)] + solve_args[2:])
     lib.nlb_vecfcn_eval_batch.argtypes = [vp, i32, i64, i32, i32, vp, vp, vp, vp, vp]
     lib.nlb_jacobian_batch.argtypes = [vp, C.POINTER(nlb_params), i32, i64, i32, i32, vp, vp, vp, vp, vp]
     lib.nlb_reduce_stats.argtypes = [vp, i64, vp, vp, vp, vp]

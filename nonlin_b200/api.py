@@ -399,11 +399,15 @@ class equation_solver:
         eng = self._engine or default_engine(_device_of(x, fvec, args, ib, status) or 0)
         p = self._params(fcn)
         entry = getattr(_LIB, self._entry)
-        eng.check(entry(eng._h, C.byref(p), fcn._fcn_id, B, m, n, _ptr(x), _ptr(fvec), _ptr(args), _ptr(fcn._shared),
-                        _ptr(ib), _ptr(status),
+        eng.check(entry(eng._h, C.byref(p), *self._extra_args(n), fcn._fcn_id, B, m, n, _ptr(x), _ptr(fvec), _ptr(args),
+                        _ptr(fcn._shared), _ptr(ib), _ptr(status),
                         C.c_void_p(stream) if stream is not None else _stream_of(x, fvec, args, ib, status)))
         self.last_fvec = fvec
         return status
+
+    def _extra_args(self, n):
+        """Solver-specific arguments that follow `params` in the C entry point (none for most solvers)."""
+        return ()
 
 
 class least_squares_solver(equation_solver):
@@ -427,6 +431,79 @@ class least_squares_solver(equation_solver):
         p = super()._params(fcn)
         p.lm_factor = self._factor
         return p
+
+
+class constrained_equation_solver(equation_solver):
+    """Adds the variable limits (reference src/nonlin_least_squares.f90:34-48, ces_* :794-883)."""
+
+    def __init__(self, engine=None):
+        super().__init__(engine)
+        self._upper = None
+        self._lower = None
+
+    def get_upper_limits(self):
+        return np.empty(0) if self._upper is None else self._upper.copy()
+
+    def set_upper_limits(self, x):
+        self._upper = np.array(x, dtype=np.float64).ravel()
+
+    def get_lower_limits(self):
+        return np.empty(0) if self._lower is None else self._lower.copy()
+
+    def set_lower_limits(self, x):
+        self._lower = np.array(x, dtype=np.float64).ravel()
+
+    def apply_limits(self, x):
+        """Clamp x (n,) or (n, B) host array into the limits, lower first (ces_apply_limits :858-883)."""
+        if self._lower is not None:
+            k = min(x.shape[0], self._lower.size)
+            lo = self._lower[:k].reshape((k,) + (1,) * (x.ndim - 1))
+            np.copyto(x[:k], lo, where=x[:k] < lo)
+        if self._upper is not None:
+            k = min(x.shape[0], self._upper.size)
+            hi = self._upper[:k].reshape((k,) + (1,) * (x.ndim - 1))
+            np.copyto(x[:k], hi, where=x[:k] > hi)
+        return x
+
+
+class constrained_least_squares_solver(constrained_equation_solver):
+    """Bounded trust-region dogleg (reference src/nonlin_least_squares.f90:50-75, cls_solve :938-1176)."""
+
+    _entry = "nlb_constrained_least_squares_solve_batch"
+
+    def __init__(self, engine=None):
+        super().__init__(engine)
+        self._delta = 1.0
+        self._scaling = 1.0
+
+    def get_trust_region_radius(self):
+        return self._delta
+
+    def set_trust_region_radius(self, x):
+        # non-positive -> 1, src/nonlin_least_squares.f90:898-910
+        x = float(x)
+        self._delta = 1.0 if x <= 0.0 else x
+
+    def get_step_scaling_factor(self):
+        return self._scaling
+
+    def set_step_scaling_factor(self, x):
+        # non-positive -> 1, src/nonlin_least_squares.f90:923-935
+        x = float(x)
+        self._scaling = 1.0 if x <= 0.0 else x
+
+    def _extra_args(self, n):
+        o = _lib.nlb_constrained_options()
+        _LIB.nlb_constrained_options_default(C.byref(o))
+        o.trust_region_radius = self._delta
+        o.step_scaling_factor = self._scaling
+        # a limit array of the wrong length is replaced by -huge / +huge, as cls_solve does (:1014-1024)
+        if self._lower is not None and self._lower.size == n:
+            o.lower = self._lower.ctypes.data
+        if self._upper is not None and self._upper.size == n:
+            o.upper = self._upper.ctypes.data
+        self._options = o            # keeps the struct (and through self the arrays) alive across the call
+        return (C.byref(o),)
 
 
 class line_search_solver(equation_solver):

@@ -10,6 +10,7 @@
 #include <string>
 
 #include "coop_kernels.cuh"
+#include "tps_cls.cuh"
 #include "tps_lm.cuh"
 #include "tps_newton_broyden.cuh"
 
@@ -38,7 +39,7 @@ struct nlb_handle {
 
 namespace {
 
-enum Solver { SOLVER_LM = 0, SOLVER_NEWTON = 1, SOLVER_BROYDEN = 2 };
+enum Solver { SOLVER_LM = 0, SOLVER_NEWTON = 1, SOLVER_BROYDEN = 2, SOLVER_CLS = 3 };
 
 int set_err(nlb_handle* h, int code, const char* what, cudaError_t ce = cudaSuccess) {
     if (h) {
@@ -159,6 +160,39 @@ tps_solve_kernel(DevParams p, long long nsys, long long B, double* __restrict__ 
         o.converge_on_chng = st.cx;
         o.converge_on_zero_diff = st.cg;
         ib[b] = o;
+    }
+    if (status) status[b] = st.status;
+}
+
+// constrained_least_squares_solver: same mapping, the limits and the radius travel by value.
+template <class F>
+__global__ void __launch_bounds__(TPS_BLOCK)
+tps_cls_kernel(DevParams p, DevCls o, long long nsys, long long B, double* __restrict__ x, double* __restrict__ fvec,
+               const double* __restrict__ sys, const double* __restrict__ shared,
+               nlb_iteration_behavior* __restrict__ ib, int32_t* __restrict__ status) {
+    constexpr int M = F::M, N = F::N;
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= nsys) return;
+    double xl[N], fl[M];
+#pragma unroll
+    for (int j = 0; j < N; ++j) xl[j] = x[j * B + b];
+    SysCtx c{sys ? sys + b : nullptr, shared, B, M, N};
+    SolveStats st;
+    tps_cls_solve<F>(p, o, c, xl, fl, st);
+#pragma unroll
+    for (int j = 0; j < N; ++j) x[j * B + b] = xl[j];
+#pragma unroll(M <= 8 ? M : 1)
+    for (int i = 0; i < M; ++i) fvec[i * B + b] = fl[i];
+    if (ib) {
+        nlb_iteration_behavior o2;
+        o2.iter_count = st.iter;
+        o2.fcn_count = st.nfev;
+        o2.jacobian_count = st.njac;
+        o2.gradient_count = 0;
+        o2.converge_on_fcn = st.cf;
+        o2.converge_on_chng = st.cx;
+        o2.converge_on_zero_diff = st.cg;
+        ib[b] = o2;
     }
     if (status) status[b] = st.status;
 }
@@ -365,6 +399,25 @@ int dispatch_tps(nlb_handle* h, int fcn_id, const DevParams& p, long long nsys, 
     }
 }
 
+int dispatch_cls(nlb_handle* h, int fcn_id, const DevParams& p, const DevCls& o, long long nsys, long long B, double* x,
+                 double* fvec, const double* sys, const double* shared, nlb_iteration_behavior* ib, int32_t* status,
+                 cudaStream_t s) {
+    if (nsys == 0) return NLB_OK;
+    const unsigned grid = (unsigned)((nsys + TPS_BLOCK - 1) / TPS_BLOCK);
+    switch (fcn_id) {
+#define X(F)                                                                                                  \
+    case F::ID:                                                                                               \
+        tps_cls_kernel<F><<<grid, TPS_BLOCK, 0, s>>>(p, o, nsys, B, x, fvec, sys, shared, ib, status);        \
+        break;
+        NLB_FIXED_FCNS(X)
+#undef X
+        default: return set_err(h, NLB_ERR_UNSUPPORTED, "no constrained least-squares kernel for this residual");
+    }
+    ++h->launches;
+    NLB_CUDA(h, cudaGetLastError());
+    return NLB_OK;
+}
+
 int check_sizes(nlb_handle* h, int fcn_id, int* m, int* n, int* sys_len, int* shared_len) {
     if (fcn_id < 0 || fcn_id >= FCN_COUNT) return set_err(h, NLB_ERR_UNKNOWN_FCN, "unknown residual id");
     const FcnInfo& fi = fcn_table()[fcn_id];
@@ -389,15 +442,16 @@ int ensure_device(nlb_handle* h) {
 
 int solve_batch(nlb_handle* h, int solver, const nlb_params* params, int fcn_id, int64_t B, int m, int n, double* x,
                 double* fvec, const double* sys, const double* shared, nlb_iteration_behavior* ib, int32_t* status,
-                void* stream) {
+                void* stream, const DevCls* cls = nullptr) {
     if (!h) return NLB_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(h->mu);
     if (!params || B < 0 || (B > 0 && (!x || !fvec))) return set_err(h, NLB_ERR_INVALID_ARGUMENT, "null argument or B < 0");
     int sys_len, shared_len;
     int rc = check_sizes(h, fcn_id, &m, &n, &sys_len, &shared_len);
     if (rc) return rc;
-    if (solver == SOLVER_LM && n > m) return set_err(h, NLB_ERR_SIZE, "least squares needs m >= n");
-    if (solver != SOLVER_LM && n != m) return set_err(h, NLB_ERR_SIZE, "Newton / quasi-Newton need m == n");
+    const bool lsq = solver == SOLVER_LM || solver == SOLVER_CLS;
+    if (lsq && n > m) return set_err(h, NLB_ERR_SIZE, "least squares needs m >= n");
+    if (!lsq && n != m) return set_err(h, NLB_ERR_SIZE, "Newton / quasi-Newton need m == n");
     if (sys_len > 0 && B > 0 && !sys) return set_err(h, NLB_ERR_INVALID_ARGUMENT, "this residual needs per-system data");
     if (shared_len > 0 && B > 0 && !shared) return set_err(h, NLB_ERR_INVALID_ARGUMENT, "this residual needs shared data");
     rc = ensure_device(h);
@@ -435,7 +489,11 @@ int solve_batch(nlb_handle* h, int solver, const nlb_params* params, int fcn_id,
         int32_t* dst = a[4].st.dev ? (int32_t*)a[4].st.dev + b0 : nullptr;
         const double* dsh = (const double*)ash.dev;
         int r;
-        if (fi.m != 0 && fi.n != 0) {
+        if (solver == SOLVER_CLS) {
+            r = (fi.m != 0 && fi.n != 0)
+                    ? dispatch_cls(h, fcn_id, p, *cls, cnt, B, dx, df, ds, dsh, dib, dst, st)
+                    : set_err(h, NLB_ERR_UNSUPPORTED, "constrained least squares: fixed-size residuals only");
+        } else if (fi.m != 0 && fi.n != 0) {
             switch (solver) {
                 case SOLVER_LM: r = dispatch_tps<SOLVER_LM>(h, fcn_id, p, cnt, B, dx, df, ds, dsh, dib, dst, st); break;
                 case SOLVER_NEWTON: r = dispatch_tps<SOLVER_NEWTON>(h, fcn_id, p, cnt, B, dx, df, ds, dsh, dib, dst, st); break;
@@ -595,6 +653,36 @@ int nlb_quasi_newton_solve_batch(nlb_handle* h, const nlb_params* params, int fc
                                  double* x, double* fvec, const double* sys, const double* shared,
                                  nlb_iteration_behavior* ib, int32_t* status, void* stream) {
     return solve_batch(h, SOLVER_BROYDEN, params, fcn_id, B, m, n, x, fvec, sys, shared, ib, status, stream);
+}
+
+void nlb_constrained_options_default(nlb_constrained_options* o) {
+    if (!o) return;
+    o->trust_region_radius = 1.0;
+    o->step_scaling_factor = 1.0;
+    o->lower = nullptr;
+    o->upper = nullptr;
+}
+
+int nlb_constrained_least_squares_solve_batch(nlb_handle* h, const nlb_params* params,
+                                              const nlb_constrained_options* options, int fcn_id, int64_t B, int m,
+                                              int n, double* x, double* fvec, const double* sys, const double* shared,
+                                              nlb_iteration_behavior* ib, int32_t* status, void* stream) {
+    if (!h) return NLB_ERR_INVALID_ARGUMENT;
+    if (!options) return set_err(h, NLB_ERR_INVALID_ARGUMENT, "null options");
+    if (fcn_id < 0 || fcn_id >= FCN_COUNT) return set_err(h, NLB_ERR_UNKNOWN_FCN, "unknown residual id");
+    const FcnInfo& fi = fcn_table()[fcn_id];
+    const int nv = fi.n != 0 ? fi.n : n;
+    if (nv <= 0 || nv > CLS_MAX_N) return set_err(h, NLB_ERR_UNSUPPORTED, "constrained least squares: n <= 8");
+    DevCls o;
+    // cls_set_radius / cls_set_factor: a non-positive value selects 1 (least_squares:902-909, 927-934)
+    o.radius = options->trust_region_radius > 0.0 ? options->trust_region_radius : 1.0;
+    o.scaling = options->step_scaling_factor > 0.0 ? options->step_scaling_factor : 1.0;
+    const double huge = 1.7976931348623157e+308;
+    for (int i = 0; i < CLS_MAX_N; ++i) {
+        o.xl[i] = (options->lower && i < nv) ? options->lower[i] : -huge;
+        o.xu[i] = (options->upper && i < nv) ? options->upper[i] : huge;
+    }
+    return solve_batch(h, SOLVER_CLS, params, fcn_id, B, m, n, x, fvec, sys, shared, ib, status, stream, &o);
 }
 
 int nlb_vecfcn_eval_batch(nlb_handle* h, int fcn_id, int64_t B, int m, int n, const double* x, double* fvec,

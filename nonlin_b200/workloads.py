@@ -4,7 +4,7 @@ Pure input generation (numpy, host): the same arrays are fed to the engine, to t
 in the tests, and to bench.py.  Nothing here computes a solution.
 
 Each workload is a dict:
-    solver   "least_squares" | "newton" | "quasi_newton"
+    solver   "least_squares" | "newton" | "quasi_newton" | "constrained_least_squares"
     fcn      registered residual name
     m, n     system size
     x0       (n, B) float64 starting points, system index fastest
@@ -112,6 +112,25 @@ def lm_expdecay4(B, m=64, seed=6, noise=1e-2):
                 bytes_per_system=_bytes(m, 4, m))
 
 
+def cls1_bounded_polyfit(B, seed=7):
+    """CLS1: the C1 cubic fits through constrained_least_squares_solver, coefficients boxed to [-10, 10]
+    (limits inactive at the solution, Coleman-Li scaling live), start 0.5."""
+    w = c1_lm_polyfit(B, seed)
+    w.update(name="CLS1", solver="constrained_least_squares", x0=np.full((4, B), 0.5),
+             settings={"set_lower_limits": [-10.0] * 4, "set_upper_limits": [10.0] * 4})
+    return w
+
+
+def cls2_bounded_2x2(B, seed=8):
+    """CLS2: README Example 1 system in the box [0, 6]^2, starts U(0.2, 5.8)^2 (root (5, 3) inside the box)."""
+    rng = np.random.default_rng(seed)
+    x0 = rng.uniform(0.2, 5.8, size=(2, B))
+    return dict(name="CLS2", solver="constrained_least_squares", fcn="misc_2fcn", m=2, n=2,
+                x0=np.ascontiguousarray(x0), args=None, shared=None,
+                settings={"set_lower_limits": [0.0, 0.0], "set_upper_limits": [6.0, 6.0]},
+                bytes_per_system=_bytes(2, 2, 0))
+
+
 WORKLOADS = {
     "C1": c1_lm_polyfit,
     "C2": c2_broyden_2x2,
@@ -119,4 +138,6 @@ WORKLOADS = {
     "C4": c4_lm_rational,
     "C5": c5_broyden_rosenbrock,
     "LM4": lm_expdecay4,
+    "CLS1": cls1_bounded_polyfit,
+    "CLS2": cls2_bounded_2x2,
 }

@@ -140,6 +140,17 @@ void la_dgemv_t(int m, int n, real alpha, const real* a, int lda, const real* x,
     }
 }
 
+// DGEMV('N') with beta = 0: y := alpha A x.  Column sweep, y(i) += (alpha x(j)) a(i,j), j outermost.
+void la_dgemv_n(int m, int n, real alpha, const real* a, int lda, const real* x, real* y) {
+    if (m == 0 || n == 0) return;
+    for (int i = 1; i <= m; ++i) y[i - 1] = 0.0;   // beta = 0
+    if (alpha == real(0.0)) return;
+    for (int j = 1; j <= n; ++j) {
+        real temp = alpha * x[j - 1];
+        for (int i = 1; i <= m; ++i) y[i - 1] = y[i - 1] + temp * AT(a, lda, i, j);
+    }
+}
+
 void la_dger(int m, int n, real alpha, const real* x, const real* y, real* a, int lda) {
     if (m == 0 || n == 0 || alpha == real(0.0)) return;
     for (int j = 1; j <= n; ++j) {
@@ -162,6 +173,18 @@ void la_dlarf_left(int m, int n, const real* v, int incv, real tau, real* c, int
         // work(1:lastc) = C(1:lastv,1:lastc)^T v ; C -= tau v work^T      (incv == 1 here)
         la_dgemv_t(lastv, lastc, real(1.0), c, ldc, v, work);
         la_dger(lastv, lastc, -tau, v, work, c, ldc);
+    }
+}
+
+// DORM2R('L','T') on one right-hand side: c := Q^T c = H(k) ... H(1) c, reflectors applied in the order
+// i = 1..k, each through DLARF with the unit diagonal entry put in place for the call.
+void la_dorm2r_lt_vec(int m, int k, real* a, int lda, const real* tau, real* c) {
+    real work[1];
+    for (int i = 1; i <= k; ++i) {
+        real aii = AT(a, lda, i, i);
+        AT(a, lda, i, i) = 1.0;
+        la_dlarf_left(m - i + 1, 1, &AT(a, lda, i, i), 1, tau[i - 1], &c[i - 1], m, work);
+        AT(a, lda, i, i) = aii;
     }
 }
 

@@ -16,6 +16,10 @@
 //   mtx_mult(.true.,...) -> DGEMV('T')
 //   solve_triangular_system(upper, no-trans, non-unit) -> DTRSV('U','N','N')
 //   qr_rank1_update      -> QRUPDATE DQR1UP (DQRTV1, DQRQH, DQROT, DAXPY, DQHQR; DLARTG)
+// and, for constrained_least_squares_solver (src/nonlin_least_squares.f90:1061,1341,1344,1351,1399):
+//   qr_factor(a, tau=, qr=) -> copy then DGEQR2 (DGEQRF takes the unblocked path for k < NB = 32)
+//   solve_qr(qr, tau, b)    -> DORM2R('L','T') (DORMQR is unblocked for k <= NB) then DTRSV('U','N','N')
+//   dgemv('T'|'N')          -> Reference BLAS DGEMV
 //
 // PARITY UNPINNED at bit level for this boundary: the reference's tests pin it only through
 // converged roots (1e-5..1e-6) and the README Example 1 counts (11/15/1), which this
@@ -55,6 +59,10 @@ void la_dger(int m, int n, real alpha, const real* x, const real* y, real* a, in
 void la_drscl(int n, real sa, real* x);
 // DGEMV('T'): y := alpha A^T x + beta y  (beta is 0 at every call site of the reference).
 void la_dgemv_t(int m, int n, real alpha, const real* a, int lda, const real* x, real* y);
+// DGEMV('N'): y := alpha A x  (beta is 0 at every call site of the reference).
+void la_dgemv_n(int m, int n, real alpha, const real* a, int lda, const real* x, real* y);
+// DORM2R('L','T') for one right-hand side: c := Q^T c with Q held as k reflectors in a / tau.
+void la_dorm2r_lt_vec(int m, int k, real* a, int lda, const real* tau, real* c);
 // DTRSV('U','N','N'): solve R x = b in place.
 void la_dtrsv_unn(int n, const real* a, int lda, real* x);
 // QRUPDATE DQR1UP with a full (k = m) Q: Q R + u v^T -> Q1 R1.  w has 2m entries.

@@ -32,6 +32,17 @@ class Params(C.Structure):
     ]
 
 
+class ClsOptions(C.Structure):
+    """constrained_least_squares_solver's own settings (radius, step scaling) and the limit arrays."""
+
+    _fields_ = [
+        ("trust_region_radius", C.c_double),
+        ("step_scaling_factor", C.c_double),
+        ("lower", C.c_void_p),
+        ("upper", C.c_void_p),
+    ]
+
+
 IB_DTYPE = np.dtype(
     [
         ("iter_count", "<i4"),
@@ -76,6 +87,8 @@ class Oracle:
         lib.nlo_eval_fcn.restype = C.c_int
         lib.nlo_jacobian.restype = C.c_int
         lib.nlo_dgesv.restype = C.c_int
+        lib.nlo_cls_solve.restype = C.c_int
+        lib.nlo_cls_solve_batch.restype = C.c_int
 
     # -- registry -----------------------------------------------------------------------
     def fcn_id(self, name):
@@ -157,6 +170,65 @@ class Oracle:
         st = self.lib.nlo_solve(SOLVERS[solver] if isinstance(solver, str) else solver, fid, m, n, C.byref(p),
                                 self._ptr(x), self._ptr(f), self._ptr(sys), self._ptr(shared), self._ptr(ib))
         return x, f, {k: int(ib[0][k]) for k in IB_DTYPE.names}, st
+
+    def _cls_options(self, lower, upper, trust_region_radius, step_scaling_factor, n):
+        o = ClsOptions()
+        self.lib.nlo_cls_options_default(C.byref(o))
+        if trust_region_radius is not None:
+            o.trust_region_radius = trust_region_radius
+        if step_scaling_factor is not None:
+            o.step_scaling_factor = step_scaling_factor
+        keep = []
+        for name, v in (("lower", lower), ("upper", upper)):
+            if v is not None:
+                a = np.ascontiguousarray(v, dtype=np.float64)
+                if a.size != n:
+                    raise ValueError("%s must have n entries" % name)
+                keep.append(a)
+                setattr(o, name, a.ctypes.data)
+        return o, keep
+
+    def cls_solve(self, fcn, x0, m=0, sys=None, shared=None, params=None, lower=None, upper=None,
+                  trust_region_radius=None, step_scaling_factor=None):
+        """constrained_least_squares_solver, one system. Returns (x, fvec, ib(dict), status)."""
+        fid = self.fcn_id(fcn) if isinstance(fcn, str) else fcn
+        info = self.fcn_info(fid)
+        x = np.array(x0, dtype=np.float64)
+        n = info["n"] or x.size
+        m = info["m"] or m or n
+        f = np.zeros(m)
+        ib = np.zeros(1, dtype=IB_DTYPE)
+        p = params or self.params()
+        o, keep = self._cls_options(lower, upper, trust_region_radius, step_scaling_factor, n)
+        sys = None if sys is None else np.ascontiguousarray(sys, dtype=np.float64)
+        shared = None if shared is None else np.ascontiguousarray(shared, dtype=np.float64)
+        st = self.lib.nlo_cls_solve(fid, m, n, C.byref(p), C.byref(o), self._ptr(x), self._ptr(f), self._ptr(sys),
+                                    self._ptr(shared), self._ptr(ib))
+        return x, f, {k: int(ib[0][k]) for k in IB_DTYPE.names}, st
+
+    def cls_solve_batch(self, fcn, x0, m=0, sys=None, shared=None, params=None, lower=None, upper=None,
+                        trust_region_radius=None, step_scaling_factor=None, nthreads=0):
+        """x0: (n, B) SoA. Returns (x (n,B), fvec (m,B), ib (B,) structured, status (B,))."""
+        fid = self.fcn_id(fcn) if isinstance(fcn, str) else fcn
+        info = self.fcn_info(fid)
+        x = np.array(x0, dtype=np.float64, order="C")
+        n, B = x.shape
+        if info["n"] and info["n"] != n:
+            raise ValueError("n mismatch")
+        m = info["m"] or m or n
+        f = np.zeros((m, B))
+        ib = np.zeros(B, dtype=IB_DTYPE)
+        status = np.zeros(B, dtype=np.int32)
+        p = params or self.params()
+        o, keep = self._cls_options(lower, upper, trust_region_radius, step_scaling_factor, n)
+        sys = None if sys is None else np.ascontiguousarray(sys, dtype=np.float64)
+        shared = None if shared is None else np.ascontiguousarray(shared, dtype=np.float64)
+        rc = self.lib.nlo_cls_solve_batch(fid, C.c_long(B), m, n, C.byref(p), C.byref(o), self._ptr(x), self._ptr(f),
+                                          self._ptr(sys), self._ptr(shared), self._ptr(ib), self._ptr(status),
+                                          int(nthreads))
+        if rc:
+            raise RuntimeError("nlo_cls_solve_batch -> %d" % rc)
+        return x, f, ib, status
 
     def solve_batch(self, solver, fcn, x0, m=0, sys=None, shared=None, params=None, nthreads=0):
         """x0: (n, B) SoA. Returns (x (n,B), fvec (m,B), ib (B,) structured, status (B,))."""

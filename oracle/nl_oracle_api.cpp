@@ -153,6 +153,65 @@ int nlo_solve(int solver, int fcn_id, int m, int n, const Params* prm, double* x
     return st;
 }
 
+// constrained_least_squares_solver, one system.  lower / upper: n entries each or null.
+void nlo_cls_options_default(ClsOptions* o) { cls_options_default(o); }
+
+int nlo_cls_solve(int fcn_id, int m, int n, const Params* prm, const ClsOptions* opt, double* x, double* fvec,
+                  const double* sys, const double* shared, IterBehavior* ib) {
+    const Problem* p = nl_problem(fcn_id);
+    int sl;
+    int rc = resolve_sizes(p, &m, &n, &sl);
+    if (rc) return rc;
+    FcnCtx c = {m, n, R(sys), R(shared)};
+    Workspace ws;
+#ifdef NL_COUNT_FLOPS
+    g_flops = 0;
+#endif
+    int st = cls_solve(p, &c, prm, opt, R(x), R(fvec), ib, &ws);
+#ifdef NL_COUNT_FLOPS
+    g_flops_total += g_flops;
+#endif
+    return st;
+}
+
+int nlo_cls_solve_batch(int fcn_id, long B, int m, int n, const Params* prm, const ClsOptions* opt, double* x,
+                        double* fvec, const double* sys, const double* shared, IterBehavior* ib, int32_t* status,
+                        int nthreads) {
+    const Problem* p = nl_problem(fcn_id);
+    int sl;
+    int rc = resolve_sizes(p, &m, &n, &sl);
+    if (rc) return rc;
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+    nthreads = 1;
+#endif
+#pragma omp parallel num_threads(nthreads)
+    {
+        Workspace ws;
+        std::vector<real> xl(n), fl(m), sl_buf(sl > 0 ? sl : 1);
+#ifdef NL_COUNT_FLOPS
+        g_flops = 0;
+#endif
+#pragma omp for schedule(dynamic, 64)
+        for (long b = 0; b < B; ++b) {
+            for (int j = 0; j < n; ++j) xl[j] = R(x)[(long)j * B + b];
+            for (int k = 0; k < sl; ++k) sl_buf[k] = R(sys)[(long)k * B + b];
+            FcnCtx c = {m, n, sl > 0 ? sl_buf.data() : nullptr, R(shared)};
+            IterBehavior lib;
+            int st = cls_solve(p, &c, prm, opt, xl.data(), fl.data(), &lib, &ws);
+            for (int j = 0; j < n; ++j) R(x)[(long)j * B + b] = xl[j];
+            for (int i = 0; i < m; ++i) R(fvec)[(long)i * B + b] = fl[i];
+            if (ib) ib[b] = lib;
+            if (status) status[b] = st;
+        }
+#ifdef NL_COUNT_FLOPS
+        g_flops_total += g_flops;
+#endif
+    }
+    return 0;
+}
+
 // B systems, SoA; one system per OpenMP thread at a time (schedule(dynamic)), workspaces
 // allocated once per thread.  Returns 0 or an API-level error; per-system codes in status[].
 int nlo_solve_batch(int solver, int fcn_id, long B, int m, int n, const Params* prm, double* x, double* fvec,

@@ -737,4 +737,259 @@ int broyden_solve(const Problem* p, const FcnCtx* c, const Params* prm, real* x,
     return NL_NO_ERROR;
 }
 
+// ---------------------------------------------------------------------------------------
+// constrained_least_squares_solver: bounded trust-region dogleg.
+//   cls_solve            src/nonlin_least_squares.f90:938-1176
+//   ces_apply_limits     :858-883
+//   alpha_box            :1181-1219
+//   coleman_li_scaling   :1222-1260
+//   scaled_norm          :1263-1273
+//   is_finite_array      :1276-1298   (tests NaN and |x| == huge only: +-Inf passes as finite)
+//   dogleg               :1301-1403
+// linalg boundary (qr_factor(a, tau=, qr=), solve_qr(qr, tau, b)): see nl_lapack.h.
+// ---------------------------------------------------------------------------------------
+void cls_options_default(ClsOptions* o) {
+    o->trust_region_radius = 1.0;      // m_delta   least_squares:64
+    o->step_scaling_factor = 1.0;      // m_scaling least_squares:66
+    o->lower = nullptr;
+    o->upper = nullptr;
+}
+
+static const double HUGE_D = DBL_MAX;  // huge(0d0)
+
+static void apply_limits(int n, real* x, const real* xl, const real* xu) {   // :858-883
+    for (int i = 1; i <= n; ++i)
+        if (V(x, i) < V(xl, i)) V(x, i) = V(xl, i);
+    for (int i = 1; i <= n; ++i)
+        if (V(x, i) > V(xu, i)) V(x, i) = V(xu, i);
+}
+
+static bool is_finite_array(int n, const real* x) {                          // :1276-1298
+    for (int i = 1; i <= n; ++i) {
+        if (!(V(x, i) == V(x, i))) return false;
+        if (f_abs(V(x, i)) == real(HUGE_D)) return false;
+    }
+    return true;
+}
+
+real alpha_box(int n, const real* x, const real* p, const real* xl, const real* xu) {   // :1181-1219
+    real rst = HUGE_D;
+    for (int i = 1; i <= n; ++i) {
+        if (V(p, i) > ZERO) {
+            if (V(xu, i) < V(x, i)) return ZERO;
+            real a = (V(xu, i) - V(x, i)) / V(p, i);
+            if (a < rst) rst = a;
+        } else if (V(p, i) < ZERO) {
+            if (V(xl, i) > V(x, i)) return ZERO;
+            real a = (V(xl, i) - V(x, i)) / V(p, i);
+            if (a < rst) rst = a;
+        }
+    }
+    if (rst < ZERO) rst = ZERO;
+    return rst;
+}
+
+void coleman_li_scaling(int n, const real* x, const real* xl, const real* xu, real* s) {   // :1222-1260
+    const real min_scale = 1.0e-8, max_scale = 1.0e8, big = HUGE_D;
+    for (int i = 1; i <= n; ++i) {
+        real di;
+        if (V(xl, i) > -big && V(xu, i) < big) di = f_min(V(x, i) - V(xl, i), V(xu, i) - V(x, i));
+        else if (V(xl, i) > -big) di = V(x, i) - V(xl, i);
+        else if (V(xu, i) < big) di = V(xu, i) - V(x, i);
+        else di = ONE;
+        di = f_max(di, min_scale);
+        V(s, i) = ONE / di;
+        if (V(s, i) > max_scale) V(s, i) = max_scale;
+    }
+}
+
+static real scaled_norm(int n, const real* x, const real* s, real* tmp) {    // :1263-1273
+    for (int i = 1; i <= n; ++i) V(tmp, i) = V(x, i) * V(s, i);
+    return f_norm2(tmp, n);
+}
+
+// wrk: 5n + 2m entries (pgn, psd, u, v, tmp, Jg, rhs)
+void dogleg(int m, int n, real delta, const real* x, const real* f, const real* jac, real* qr, const real* tau,
+            const real* s, const real* xl, const real* xu, real* p, real* g, real* Jp, real* prered, real* wrk) {
+    real* pgn = wrk;
+    real* psd = pgn + n;
+    real* u = psd + n;
+    real* v = u + n;
+    real* tmp = v + n;
+    real* Jg = tmp + n;
+    real* rhs = Jg + m;
+    real alpha;
+    la_dgemv_t(m, n, ONE, jac, m, f, g);                                     // :1341
+    for (int i = 1; i <= m; ++i) V(rhs, i) = V(f, i);                        // :1344  u = solve_qr(qr, tau, f)
+    la_dorm2r_lt_vec(m, n, qr, m, tau, rhs);
+    la_dtrsv_unn(n, qr, m, rhs);
+    for (int i = 1; i <= n; ++i) V(u, i) = V(rhs, i);
+    for (int i = 1; i <= n; ++i) V(pgn, i) = -V(u, i);
+    real pgnnorm = scaled_norm(n, pgn, s, tmp);
+    if (pgnnorm > delta) {                                                   // :1349
+        la_dgemv_n(m, n, ONE, jac, m, g, Jg);
+        real c1 = f_dot(g, g, n);
+        real c2 = f_dot(Jg, Jg, m);
+        if (c2 > ZERO && c1 > ZERO) alpha = c1 / c2;
+        else alpha = ZERO;
+        for (int i = 1; i <= n; ++i) V(psd, i) = -alpha * V(g, i);
+        real psdnorm = scaled_norm(n, psd, s, tmp);
+        if (psdnorm >= delta && psdnorm > ZERO) {
+            real sc = delta / psdnorm;
+            for (int i = 1; i <= n; ++i) V(p, i) = sc * V(psd, i);
+        } else {
+            for (int i = 1; i <= n; ++i) V(u, i) = V(pgn, i) - V(psd, i);
+            for (int i = 1; i <= n; ++i) V(u, i) = V(s, i) * V(u, i);
+            for (int i = 1; i <= n; ++i) V(v, i) = V(s, i) * V(psd, i);
+            real a = f_dot(u, u, n);
+            real b = real(2.0) * f_dot(u, v, n);
+            real cq = f_dot(v, v, n) - delta * delta;
+            if (a <= ZERO) {
+                for (int i = 1; i <= n; ++i) V(p, i) = V(psd, i);
+            } else {
+                real t;
+                real arg = f_max(ZERO, b * b - real(4.0) * a * cq);
+                if (arg == ZERO) {
+                    t = -b / (real(2.0) * a);
+                } else {
+                    t = (-b + f_sqrt(arg)) / (real(2.0) * a);
+                    if (t < ZERO || t > ONE) t = (-b - f_sqrt(arg)) / (real(2.0) * a);
+                }
+                t = f_max(ZERO, f_min(ONE, t));
+                for (int i = 1; i <= n; ++i) V(p, i) = V(psd, i) + t * V(u, i);   // u is the *scaled* difference (:1384)
+            }
+        }
+    } else {
+        for (int i = 1; i <= n; ++i) V(p, i) = V(pgn, i);
+    }
+    alpha = alpha_box(n, x, p, xl, xu);                                      // :1393-1396
+    if (alpha < ONE)
+        for (int i = 1; i <= n; ++i) V(p, i) = alpha * V(p, i);
+    la_dgemv_n(m, n, ONE, jac, m, p, Jp);                                    // :1399-1402
+    real c1 = f_dot(g, p, n);
+    real c2 = HALF * f_dot(Jp, Jp, m);
+    *prered = -c1 - c2;
+}
+
+int cls_solve(const Problem* p, const FcnCtx* c, const Params* prm, const ClsOptions* opt, real* x, real* fvec,
+              IterBehavior* ib, Workspace* ws) {
+    const real delta_max = 1.0e3, eta = 1.0e-1, ls_cl = 1.0e-4, ls_beta = 0.5;
+    const int ls_max_iter = 10;
+    const int neqn = c->m, nvar = c->n;
+    bool converged = false, xcnvrg = false, fcnvrg = false, gcnvrg = false;
+    int neval = 0, iter = 0, njac = 0;
+    const real ftol = prm->fcn_tol, xtol = prm->var_tol, gtol = prm->grad_tol;
+    const int maxeval = prm->max_fcn_evals;
+    ib->iter_count = 0; ib->fcn_count = 0; ib->jacobian_count = 0; ib->gradient_count = 0;   // :993-1001
+    ib->converge_on_fcn = 0; ib->converge_on_chng = 0; ib->converge_on_zero_diff = 0;
+    if (nvar > neqn) return NL_UNDERDEFINED_PROBLEM_ERROR;                   // :1005
+
+    const size_t mn = (size_t)neqn * nvar;
+    real* base = ws->get(2 * mn + 12 * (size_t)nvar + 5 * (size_t)neqn);
+    real* jac = base;
+    real* qr = jac + mn;
+    real* tau = qr + mn;
+    real* s = tau + nvar;
+    real* g = s + nvar;
+    real* pv = g + nvar;
+    real* xnew = pv + nvar;
+    real* xl = xnew + nvar;
+    real* xu = xl + nvar;
+    real* Jp = xu + nvar;
+    real* fnew = Jp + neqn;
+    real* fdw = fnew + neqn;
+    real* dwrk = fdw + neqn;                            // 5n + 2m
+    real qrwork[1];
+    (void)qrwork;
+
+    for (int i = 1; i <= nvar; ++i) {                                        // :1014-1024
+        V(xl, i) = opt->lower ? real(opt->lower[i - 1]) : real(-HUGE_D);
+        V(xu, i) = opt->upper ? real(opt->upper[i - 1]) : real(HUGE_D);
+    }
+
+    apply_limits(nvar, x, xl, xu);                                           // :1038-1045
+    p->fcn(x, fvec, c);
+    neval = 1;
+    real fnorm = f_norm2(fvec, neqn);
+    real xnorm = f_norm2(x, nvar);
+    if (!is_finite_array(nvar, x) || !is_finite_array(neqn, fvec)) return NL_NO_ERROR;   // early return, ib stays zero
+
+    real delta = opt->trust_region_radius;                                   // :1048
+    iter = 1;
+    for (;;) {
+        fd_jacobian(p, c, prm, x, jac, fvec, fdw);                           // :1052-1053
+        ++njac;
+        for (size_t e = 0; e < mn; ++e) qr[e] = jac[e];                      // :1061
+        la_dgeqr2(neqn, nvar, qr, neqn, tau, dwrk);
+        coleman_li_scaling(nvar, x, xl, xu, s);                              // :1064
+        real prered;
+        dogleg(neqn, nvar, delta, x, fvec, jac, qr, tau, s, xl, xu, pv, g, Jp, &prered, dwrk);   // :1067-1068
+        xnorm = scaled_norm(nvar, pv, s, dwrk);
+        real gnorm = f_norm2(g, nvar);
+        for (int i = 1; i <= nvar; ++i) V(xnew, i) = V(x, i) + V(pv, i);
+
+        p->fcn(xnew, fnew, c);                                               // :1074-1076
+        real fnewnorm = f_norm2(fnew, neqn);
+        ++neval;
+
+        real actred = HALF * (fnorm * fnorm - fnewnorm * fnewnorm);          // :1079-1084
+        real rho;
+        if (prered > ZERO && actred >= ZERO) rho = actred / prered;
+        else rho = ZERO;
+
+        if (rho < real(0.25)) {                                              // :1087-1091
+            delta = f_max(real(0.25), real(1.0e-12));
+        } else if (rho > real(0.75) && f_abs(xnorm - delta) < real(1.0e-12) * delta) {
+            delta = f_min(real(2.0) * delta, delta_max);
+        }
+
+        if (rho > eta && fnewnorm <= fnorm) {                                // :1094-1100
+            for (int i = 1; i <= nvar; ++i) V(x, i) = V(xnew, i);
+            apply_limits(nvar, x, xl, xu);
+            for (int i = 1; i <= neqn; ++i) V(fvec, i) = V(fnew, i);
+            fnorm = fnewnorm;
+            ++iter;
+        } else {                                                             // :1101-1134
+            real dderiv = f_dot(g, pv, nvar);
+            if (dderiv >= ZERO) {
+                delta = f_max(HALF * delta, real(1.0e-12));
+            } else {
+                real stepscale = opt->step_scaling_factor;
+                int k;
+                for (k = 1; k <= ls_max_iter; ++k) {
+                    for (int i = 1; i <= nvar; ++i) V(xnew, i) = V(x, i) + stepscale * V(pv, i);
+                    apply_limits(nvar, xnew, xl, xu);
+                    p->fcn(xnew, fnew, c);
+                    ++neval;
+                    fnewnorm = f_norm2(fnew, neqn);
+                    if (fnewnorm <= fnorm + ls_cl * stepscale * dderiv) {
+                        for (int i = 1; i <= nvar; ++i) V(x, i) = V(xnew, i);
+                        for (int i = 1; i <= neqn; ++i) V(fvec, i) = V(fnew, i);
+                        fnorm = fnewnorm;
+                        ++iter;
+                        delta = f_max(stepscale * xnorm, real(1.0e-12));
+                        break;
+                    }
+                    stepscale = stepscale * ls_beta;
+                }
+                if (k > ls_max_iter) delta = f_max(HALF * delta, real(1.0e-12));
+            }
+        }
+
+        if (!is_finite_array(nvar, x) || !is_finite_array(neqn, fvec)) break;   // :1137-1139
+
+        if (xnorm <= xtol) { converged = true; xcnvrg = true; break; }       // :1142-1159
+        if (f_abs(actred) <= ftol && f_abs(prered) <= ftol && HALF * rho <= ONE) {
+            converged = true; fcnvrg = true; break;
+        }
+        if (gnorm <= gtol) { converged = true; gcnvrg = true; break; }
+        if (neval >= maxeval) break;
+    }
+    ib->iter_count = iter; ib->fcn_count = neval; ib->jacobian_count = njac;    // :1163-1170 (gradient_count stays 0)
+    ib->converge_on_fcn = fcnvrg; ib->converge_on_chng = xcnvrg; ib->converge_on_zero_diff = gcnvrg;
+    if (!converged) return NL_CONVERGENCE_ERROR;                             // :1173-1175
+    return NL_NO_ERROR;
+}
+
+
 }  // namespace nlo

@@ -12,6 +12,9 @@
 //   backtrack_min   <- min_backtrack_search   src/nonlin_linesearch.f90:495-551
 //   limit_vector    <- limit_search_vector    src/nonlin_linesearch.f90:554-572
 //   test_convergence<- test_convergence       src/nonlin_helper.f90:36-124
+//   cls_solve       <- cls_solve              src/nonlin_least_squares.f90:938-1176
+//   dogleg          <- dogleg                 src/nonlin_least_squares.f90:1301-1403
+//   alpha_box, coleman_li_scaling             src/nonlin_least_squares.f90:1181-1260
 // Where the reference executes `error stop <code>` the restatement returns <code> as the
 // per-system status and leaves x / fvec / ib at the state they had at that point.
 #ifndef NL_SOLVERS_H
@@ -87,6 +90,22 @@ void lm_par(int m, int n, real* r, int ldr, const int* ipvt, const real* diag, c
 
 int lm_solve(const Problem* p, const FcnCtx* c, const Params* prm, real* x, real* fvec, IterBehavior* ib,
              Workspace* ws);
+// constrained_least_squares_solver's own members (m_delta, m_scaling, least_squares:64-66) and the limits of
+// constrained_equation_solver (multi_eqn: m_lower / m_upper); null limits = the +-huge arrays the reference
+// fills in when none were set (least_squares:1014-1024).
+struct ClsOptions {
+    double trust_region_radius;
+    double step_scaling_factor;
+    const double* lower;
+    const double* upper;
+};
+void cls_options_default(ClsOptions* o);
+real alpha_box(int n, const real* x, const real* p, const real* xl, const real* xu);
+void coleman_li_scaling(int n, const real* x, const real* xl, const real* xu, real* s);
+void dogleg(int m, int n, real delta, const real* x, const real* f, const real* jac, real* qr, const real* tau,
+            const real* s, const real* xl, const real* xu, real* p, real* g, real* Jp, real* prered, real* wrk);
+int cls_solve(const Problem* p, const FcnCtx* c, const Params* prm, const ClsOptions* opt, real* x, real* fvec,
+              IterBehavior* ib, Workspace* ws);
 int newton_solve(const Problem* p, const FcnCtx* c, const Params* prm, real* x, real* fvec, IterBehavior* ib,
                  Workspace* ws);
 int broyden_solve(const Problem* p, const FcnCtx* c, const Params* prm, real* x, real* fvec, IterBehavior* ib,

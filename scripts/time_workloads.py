@@ -12,7 +12,8 @@ for spec in sys.argv[1:]:
     if os.environ.get("MAXEVAL"): w["settings"]["set_max_fcn_evals"] = int(os.environ["MAXEVAL"])
     obj = nb.vecfcn_helper(); obj.set_fcn(w["fcn"], w["m"], w["n"])
     if w["shared"] is not None: obj.set_shared_data(torch.from_numpy(w["shared"]).cuda())
-    s = {"least_squares": nb.least_squares_solver, "newton": nb.newton_solver, "quasi_newton": nb.quasi_newton_solver}[w["solver"]]()
+    s = {"least_squares": nb.least_squares_solver, "newton": nb.newton_solver, "quasi_newton": nb.quasi_newton_solver,
+         "constrained_least_squares": nb.constrained_least_squares_solver}[w["solver"]]()
     okw = {}
     for k, v in w["settings"].items():
         getattr(s, k)(v)
@@ -28,7 +29,11 @@ for spec in sys.argv[1:]:
     stats = eng.reduce_stats(ib, st, B)
     nsub = min(B, int(os.environ.get("CPU_SUB", "512")))
     t0 = time.time()
-    o.solve_batch(w["solver"], w["fcn"], w["x0"][:, :nsub].copy(), m=w["m"], sys=None if w["args"] is None else w["args"][:, :nsub].copy(), shared=w["shared"], params=o.params(**okw))
+    sub = dict(m=w["m"], sys=None if w["args"] is None else w["args"][:, :nsub].copy(), shared=w["shared"], params=o.params(**okw))
+    if w["solver"] == "constrained_least_squares":
+        o.cls_solve_batch(w["fcn"], w["x0"][:, :nsub].copy(), lower=w["settings"].get("set_lower_limits"), upper=w["settings"].get("set_upper_limits"), **sub)
+    else:
+        o.solve_batch(w["solver"], w["fcn"], w["x0"][:, :nsub].copy(), **sub)
     dt = time.time() - t0
     print("%s B=%d %s: gpu %.2f ms -> %.3e systems/s | cpu port %.3e systems/s (%d cores) | ratio %.1f | conv %d/%d mean iter %.1f nfev %.1f njac %.1f max iter %d" % (
         name, B, kw, best, B / best * 1e3, nsub / dt, os.cpu_count(), (B / best * 1e3) / (nsub / dt), stats["converged"], B,

@@ -31,7 +31,8 @@ def test_every_entry_point_cites_the_reference():
     # each solver / helper entry point names the reference procedure and file:line it replaces
     for proc in ("lss_solve, src/nonlin_least_squares.f90:118-391", "ns_solve, src/nonlin_solve.f90:452-638",
                  "qns_solve, src/nonlin_solve.f90:156-425", "vfh_jac_fcn, src/nonlin_multi_eqn_mult_var.f90:198-277",
-                 "vfh_fcn, src/nonlin_multi_eqn_mult_var.f90:178-195", "src/nonlin_types.f90:8-29"):
+                 "vfh_fcn, src/nonlin_multi_eqn_mult_var.f90:178-195", "src/nonlin_types.f90:8-29",
+                 "cls_solve, src/nonlin_least_squares.f90:938-1176"):
         assert proc in HEADER
 
 
@@ -49,6 +50,21 @@ def test_struct_layouts_and_defaults():
     # status codes in the header and in the Python mirror agree
     for name, val in re.findall(r"#define NLB_(\w+_ERROR) (\d+)", HEADER):
         assert getattr(_lib, "NL_" + name) == int(val)
+
+
+def test_constrained_options_struct(oracle):
+    from nonlin_b200 import _lib
+    from oracle.nl_oracle import ClsOptions
+
+    lib = _lib.load()
+    o = _lib.nlb_constrained_options()
+    lib.nlb_constrained_options_default(C.byref(o))
+    assert (o.trust_region_radius, o.step_scaling_factor, o.lower, o.upper) == (1.0, 1.0, None, None)
+    assert [f[0] for f in ClsOptions._fields_] == [f[0] for f in _lib.nlb_constrained_options._fields_]
+    assert C.sizeof(ClsOptions) == C.sizeof(_lib.nlb_constrained_options) == 32
+    block = HEADER[HEADER.index("typedef struct nlb_constrained_options {"):HEADER.index("} nlb_constrained_options;")]
+    pos = [block.index(f[0]) for f in _lib.nlb_constrained_options._fields_]
+    assert pos == sorted(pos)
 
 
 def test_params_struct_matches_oracle_struct(oracle):

@@ -21,7 +21,8 @@ COUNT_MATCH_MIN = 0.99  # north_star bar on (iter, nfev, njac) equality
 
 
 def make_solver(nb, w, **extra):
-    cls = {"least_squares": nb.least_squares_solver, "newton": nb.newton_solver, "quasi_newton": nb.quasi_newton_solver}
+    cls = {"least_squares": nb.least_squares_solver, "newton": nb.newton_solver, "quasi_newton": nb.quasi_newton_solver,
+           "constrained_least_squares": nb.constrained_least_squares_solver}
     s = cls[w["solver"]]()
     for k, v in list(w["settings"].items()) + list(extra.items()):
         getattr(s, k)(v)
@@ -532,3 +533,213 @@ def test_non_finite_and_degenerate_starts_terminate_like_the_oracle(engine, orac
         xo, fo, ibo, sto = oracle.solve_batch(solver, fcn, x0, m=m, sys=args)
     assert np.array_equal(st, sto) and np.array_equal(ib, ibo)
     assert np.array_equal(x, xo, equal_nan=True) and np.array_equal(f, fo, equal_nan=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# constrained_least_squares_solver: bounded trust-region dogleg
+# ---------------------------------------------------------------------------------------------
+def run_cls(nb, oracle, fcn, x0, m, args=None, lower=None, upper=None, radius=None, scaling=None, analytic=False,
+            **params):
+    n, B = x0.shape
+    obj = nb.vecfcn_helper()
+    obj.set_fcn(fcn, m, n)
+    if analytic:
+        obj.set_jacobian()
+    s = nb.constrained_least_squares_solver()
+    for k, v in params.items():
+        getattr(s, "set_" + {"max_fcn_evals": "max_fcn_evals", "fcn_tol": "fcn_tolerance", "var_tol": "var_tolerance",
+                             "grad_tol": "gradient_tolerance"}[k])(v)
+    if lower is not None:
+        s.set_lower_limits(lower)
+    if upper is not None:
+        s.set_upper_limits(upper)
+    if radius is not None:
+        s.set_trust_region_radius(radius)
+    if scaling is not None:
+        s.set_step_scaling_factor(scaling)
+    x = x0.copy()
+    f = np.zeros((m, B))
+    ib = nb.iteration_behavior(B)
+    st = s.solve(obj, x, f, ib, args=args)
+    ref = oracle.cls_solve_batch(fcn, x0, m=m, sys=args, lower=lower, upper=upper, trust_region_radius=radius,
+                                 step_scaling_factor=scaling,
+                                 params=oracle.params(use_analytic_jacobian=int(analytic), **params))
+    return (x, f, ib, st), ref
+
+
+def assert_identical(got, ref):
+    x, f, ib, st = got
+    xo, fo, ibo, sto = ref
+    assert np.array_equal(st, sto)
+    assert np.array_equal(x, xo, equal_nan=True) and np.array_equal(f, fo, equal_nan=True)
+    assert np.array_equal(ib.view(np.int32), ibo.view(np.int32))
+
+
+CLS_CASES = [
+    # fcn, start (lo, hi), lower, upper, extra
+    ("misc_2fcn", (0.2, 5.8), None, None, {}),
+    ("misc_2fcn", (0.2, 5.8), [0.0, 0.0], [6.0, 6.0], {}),
+    ("misc_2fcn", (0.2, 5.8), [0.0, 0.0], [4.5, 10.0], {}),                 # root cut off: ends on the face x1 = 4.5
+    ("misc_2fcn", (-8.0, 8.0), [-6.0, -6.0], [6.0, 6.0], {}),               # starts outside the box get clamped
+    ("misc_2fcn", (0.2, 5.8), [0.0, 0.0], None, {"analytic": True}),        # one-sided limits, jac1
+    ("misc_2fcn", (0.2, 5.8), None, None, {"radius": 0.05, "scaling": 0.5, "max_fcn_evals": 400}),
+    ("misc_2fcn", (0.2, 5.8), None, None, {"fcn_tol": 1e-14, "var_tol": 1e-6}),
+    ("poorly_scaled_2fcn", (0.5, 1.0), None, None, {"max_fcn_evals": 5000}),
+    ("poorly_scaled_2fcn", (0.5, 1.0), None, None, {}),                     # budget of 100: NL_CONVERGENCE_ERROR
+    ("powell_badly_scaled", (0.0, 1.0), None, None, {"max_fcn_evals": 1000}),
+    ("powell_badly_scaled", (0.0, 1.0), [0.0, 0.0], [1.0, 20.0], {"max_fcn_evals": 1000, "analytic": True}),
+    ("misc_2fcn_01", (0.1, 2.0), None, None, {}),
+    ("misc_2fcn_a", (0.2, 5.8), [0.0, 0.0], [10.0, 10.0], {}),               # per-system args
+    # polar / polar_scaled call sin and cos, which CUDA's and glibc's libm round differently: outside the bitwise set
+]
+
+
+@pytest.mark.parametrize("fcn,start,lower,upper,extra", CLS_CASES)
+def test_cls_square_parity_vs_oracle(engine, oracle, fcn, start, lower, upper, extra):
+    import nonlin_b200 as nb
+
+    B = 512 if extra.get("max_fcn_evals", 0) >= 1000 else 4096
+    rng = np.random.default_rng(11)
+    x0 = rng.uniform(start[0], start[1], size=(2, B))
+    args = None
+    obj = nb.vecfcn_helper()
+    obj.set_fcn(fcn, 2, 2)
+    if obj._info["sys_len"]:
+        args = rng.uniform(1.0, 3.0, size=(obj._info["sys_len"], B))
+    got, ref = run_cls(nb, oracle, fcn, x0, 2, args=args, lower=lower, upper=upper, **extra)
+    assert_identical(got, ref)
+
+
+@pytest.mark.parametrize("lower,upper,maxeval", [(None, None, 100), ([-10.0] * 4, [10.0] * 4, 100),
+                                                 ([0.0, -1.0, 0.0, 0.0], [1.0, 1.0, 2.0, 2.0], 100),
+                                                 ([0.0, -1.0, 0.0, 0.0], [1.0, 1.0, 2.0, 2.0], 300)])
+def test_cls_polyfit_parity_vs_oracle(engine, oracle, lower, upper, maxeval):
+    import nonlin_b200 as nb
+    from nonlin_b200 import workloads as W
+
+    B = 2048
+    w = W.WORKLOADS["C1"](B)
+    x0 = np.full((4, B), 0.5)
+    got, ref = run_cls(nb, oracle, "lsq_poly_fit", x0, 21, args=w["args"], lower=lower, upper=upper,
+                       max_fcn_evals=maxeval)
+    assert_identical(got, ref)
+    if upper is None or upper[0] > 5:
+        assert (ref[3] == 0).mean() > 0.99
+    else:
+        x = got[0]
+        assert np.all(x >= np.array(lower)[:, None]) and np.all(x <= np.array(upper)[:, None])
+
+
+@pytest.mark.parametrize("name", ["CLS1", "CLS2"])
+def test_cls_workload_parity_through_workload_table(engine, oracle, name):
+    import nonlin_b200 as nb
+    from nonlin_b200 import workloads as W
+
+    B = 4096
+    w = W.WORKLOADS[name](B)
+    x, f, ib, st = run_engine(nb, w)
+    ref = oracle.cls_solve_batch(w["fcn"], w["x0"], m=w["m"], sys=w["args"], lower=w["settings"]["set_lower_limits"],
+                                 upper=w["settings"]["set_upper_limits"])
+    assert_identical((x, f, ib, st), ref)
+    assert (st == 0).mean() > 0.99
+
+
+CLS_TABLE = [
+    # fcn, x0, analytic, lower, upper, args, maxeval, |x| expected, tol        reference test (tests/nonlin_test_solve.f90)
+    ("misc_2fcn", (0.5, 0.5), True, [-np.finfo(float).max] * 2, [np.finfo(float).max] * 2, None, 100, (5, 3), 1e-6),   # _1 :973
+    ("misc_2fcn", (1.0, 1.0), True, [-np.finfo(float).max] * 2, [np.finfo(float).max] * 2, None, 100, (5, 3), 1e-6),
+    ("poorly_scaled_2fcn", (0.5, 0.5), False, None, None, None, 5000, (5000, 10), 1e-6),                               # _2 :1028
+    ("poorly_scaled_2fcn", (1.0, 1.0), False, None, None, None, 5000, (5000, 10), 1e-6),
+    ("misc_2fcn_a", (0.5, 0.5), False, None, None, 2.0, 100, (5, 3), 1e-6),                                            # _4 :1112
+    ("misc_2fcn_a", (1.0, 1.0), True, None, None, 2.0, 100, (5, 3), 1e-6),
+    ("misc_2fcn", (1.0, 1.0), False, [4.0, 2.0], [5.6, 3.6], None, 100, (5, 3), 1e-6),                                 # _bounds :1186
+]
+
+
+@pytest.mark.parametrize("fcn,x0,analytic,lower,upper,a,maxeval,expect,tol", CLS_TABLE)
+def test_cls_reference_test_table(engine, fcn, x0, analytic, lower, upper, a, maxeval, expect, tol):
+    import nonlin_b200 as nb
+
+    B = 64
+    obj = nb.vecfcn_helper()
+    obj.set_fcn(fcn, 2, 2)
+    if analytic:
+        obj.set_jacobian()
+    s = nb.constrained_least_squares_solver()
+    s.set_max_fcn_evals(maxeval)
+    if lower is not None:
+        s.set_lower_limits(lower)
+        s.set_upper_limits(upper)
+    x = np.tile(np.array(x0, dtype=np.float64)[:, None], (1, B))
+    args = None if a is None else np.full((1, B), a)
+    st = s.solve(obj, x, args=args)
+    assert np.all(st == 0)
+    assert np.all(np.abs(np.abs(x) - np.array(expect, dtype=np.float64)[:, None]) <= tol)
+    if lower is not None and lower[0] > -1e300:
+        assert np.all(x >= np.array(lower)[:, None] - 1e-10) and np.all(x <= np.array(upper)[:, None] + 1e-10)
+
+
+def test_cls_reference_test_3_cubic_fit_agrees_with_lm(engine):
+    # test_constrained_least_squares_3 (:1080): |x_lm - x_cls| <= 1e-5 on lsfcn1 from [1, 1, 1, 1]
+    import nonlin_b200 as nb
+
+    obj = nb.vecfcn_helper()
+    obj.set_fcn("lsq_poly_fit", 21, 4)
+    from nonlin_b200.workloads import POLYFIT_YP
+
+    x = np.ones((4, 8)); xc = np.ones((4, 8))
+    y = np.ascontiguousarray(np.tile(POLYFIT_YP[:, None], (1, 8)))
+    assert np.all(nb.least_squares_solver().solve(obj, x, args=y) == 0)
+    assert np.all(nb.constrained_least_squares_solver().solve(obj, xc, args=y) == 0)
+    assert np.all(np.abs(x - xc) <= 1e-5)
+
+
+def test_cls_non_finite_starts_and_statuses(engine, oracle):
+    import nonlin_b200 as nb
+
+    rng = np.random.default_rng(21)
+    B = 1024
+    x0 = rng.uniform(0.2, 5.8, size=(2, B))
+    x0[0, ::7] = np.nan
+    x0[1, 3::11] = np.inf
+    x0[0, 5::13] = -np.inf
+    got, ref = run_cls(nb, oracle, "misc_2fcn", x0, 2)
+    assert_identical(got, ref)
+    ib = got[2]
+    bad = ~np.isfinite(x0).all(axis=0)
+    assert np.all(got[3][bad] == 0) and np.all(ib["iter_count"][bad] == 0) and np.all(ib["fcn_count"][bad] == 0)
+    assert np.all(got[0][0, 5::13] == -np.finfo(float).max)       # -Inf clamped to -huge by apply_limits, then rejected
+
+
+def test_cls_device_buffers_equal_host_buffers(engine, oracle):
+    import torch
+
+    import nonlin_b200 as nb
+    from nonlin_b200 import workloads as W
+
+    B = 4096
+    w = W.WORKLOADS["CLS1"](B)
+    xh, fh, ibh, sth = run_engine(nb, w)
+    obj = nb.vecfcn_helper()
+    obj.set_fcn(w["fcn"], w["m"], w["n"])
+    s = make_solver(nb, w)
+    xd = torch.from_numpy(w["x0"]).cuda()
+    fd = torch.zeros((w["m"], B), dtype=torch.float64, device="cuda")
+    ad = torch.from_numpy(w["args"]).cuda()
+    ibd = torch.zeros((B, 7), dtype=torch.int32, device="cuda")
+    std = s.solve(obj, xd, fd, ibd, args=ad)
+    torch.cuda.synchronize()
+    assert np.array_equal(xd.cpu().numpy(), xh) and np.array_equal(fd.cpu().numpy(), fh)
+    assert np.array_equal(ibd.cpu().numpy(), ibh.view(np.int32).reshape(B, 7))
+    assert np.array_equal(std.cpu().numpy(), sth)
+
+
+def test_cls_unsupported_residual_is_an_api_error(engine):
+    import nonlin_b200 as nb
+
+    obj = nb.vecfcn_helper()
+    obj.set_fcn("exp_decay_4", 64, 4)
+    obj.set_shared_data(np.linspace(0.0, 4.0, 64))
+    with pytest.raises(nb.NonlinError) as e:
+        nb.constrained_least_squares_solver().solve(obj, np.ones((4, 8)), args=np.ones((64, 8)))
+    assert e.value.code == nb.NLB_ERR_UNSUPPORTED

@@ -28,6 +28,30 @@ def test_lm_step_scaling_factor_clamp():
     s.set_step_scaling_factor(5.0); assert s.get_step_scaling_factor() == 5.0
 
 
+def test_constrained_least_squares_solver_settings():
+    s = nb.constrained_least_squares_solver()
+    assert isinstance(s, nb.constrained_equation_solver) and isinstance(s, nb.equation_solver)
+    assert s.get_trust_region_radius() == 1.0                    # src/nonlin_least_squares.f90:64
+    assert s.get_step_scaling_factor() == 1.0                    # :66
+    s.set_trust_region_radius(0.0); assert s.get_trust_region_radius() == 1.0       # :904-905 (x <= 0 -> 1)
+    s.set_trust_region_radius(-3.0); assert s.get_trust_region_radius() == 1.0
+    s.set_trust_region_radius(2.5); assert s.get_trust_region_radius() == 2.5
+    s.set_step_scaling_factor(-1.0); assert s.get_step_scaling_factor() == 1.0      # :929-930
+    s.set_step_scaling_factor(0.5); assert s.get_step_scaling_factor() == 0.5
+    assert s.get_lower_limits().size == 0 and s.get_upper_limits().size == 0        # :797-808 unallocated -> size 0
+    s.set_lower_limits([4.0, 2.0]); s.set_upper_limits([5.6, 3.6])
+    assert np.array_equal(s.get_lower_limits(), [4.0, 2.0]) and np.array_equal(s.get_upper_limits(), [5.6, 3.6])
+    x = np.array([1.0, 9.0])
+    assert np.array_equal(s.apply_limits(x), [4.0, 3.6])         # ces_apply_limits :858-883
+    xb = np.array([[1.0, 5.0, 7.0], [2.5, -1.0, 3.7]])
+    assert np.array_equal(s.apply_limits(xb), [[4.0, 5.0, 5.6], [2.5, 2.0, 3.6]])
+    # limits of the wrong length are ignored by the solve (cls_solve :1014-1024 replaces them by +-huge)
+    s.set_lower_limits([0.0, 0.0, 0.0])
+    (opt,) = s._extra_args(2)
+    assert opt._obj.lower is None and opt._obj.upper is not None
+    assert opt._obj.trust_region_radius == 2.5 and opt._obj.step_scaling_factor == 0.5
+
+
 def test_quasi_newton_and_line_search_settings():
     s = nb.quasi_newton_solver()
     assert s.get_jacobian_interval() == 5                        # src/nonlin_solve.f90:51

@@ -64,8 +64,12 @@ def workload_label(w, B):
         "C4": "LM curve fits m=4096 x n=16 (rational 7/8 model)",
         "C5": "extended Rosenbrock n=64, quasi_newton_solver + line search",
         "LM4": "4-parameter double-exponential LM fits, m=64",
+        "CLS1": "1M x README Example 2 cubic fit (m=21, n=4), constrained_least_squares_solver, limits [-10, 10]",
+        "CLS2": "1M x README Example 1 (2x2), constrained_least_squares_solver, box [0, 6]^2, random starts",
     }[w["name"]]
-    return "%s [BASELINE config %s], B=%d per GPU" % (desc, w["name"], B)
+    tag = "BASELINE config %s" % w["name"] if w["name"].startswith("C") and not w["name"].startswith("CLS") else (
+        "SURVEY 8(f) widening %s" % w["name"] if w["name"].startswith("CLS") else "SURVEY 6 probe %s" % w["name"])
+    return "%s [%s], B=%d per GPU" % (desc, tag, B)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -128,6 +132,14 @@ def oracle_params(o, w):
     return o.params(**kw)
 
 
+def oracle_solve_batch(o, w, x0, sysd, **kw):
+    """The oracle's batch solve for the workload's solver (constrained least squares has its own entry)."""
+    if w["solver"] == "constrained_least_squares":
+        return o.cls_solve_batch(w["fcn"], x0, m=w["m"], sys=sysd, shared=w["shared"],
+                                 lower=w["settings"].get("set_lower_limits"), upper=w["settings"].get("set_upper_limits"), **kw)
+    return o.solve_batch(w["solver"], w["fcn"], x0, m=w["m"], sys=sysd, shared=w["shared"], **kw)
+
+
 def cpu_port_throughput(w, min_seconds=4.0, max_reps=50, sample=None):
     """Time the CPU oracle (OpenMP, all host cores) on the workload's batch (or a slice of it)."""
     from oracle.nl_oracle import Oracle
@@ -139,12 +151,12 @@ def cpu_port_throughput(w, min_seconds=4.0, max_reps=50, sample=None):
     sysd = None if w["args"] is None else np.ascontiguousarray(w["args"][:, :nsub])
     p = oracle_params(o, w)
     cores = os.cpu_count() or 1
-    o.solve_batch(w["solver"], w["fcn"], x0[:, : min(nsub, 4096)].copy(), m=w["m"],
-                  sys=None if sysd is None else sysd[:, : min(nsub, 4096)].copy(), shared=w["shared"], params=p)
+    oracle_solve_batch(o, w, x0[:, : min(nsub, 4096)].copy(), None if sysd is None else sysd[:, : min(nsub, 4096)].copy(),
+                       params=p)
     reps, elapsed, conv = 0, 0.0, 0
     while (elapsed < min_seconds and reps < max_reps) or reps < 2:
         t0 = time.perf_counter()
-        _, _, _, st = o.solve_batch(w["solver"], w["fcn"], x0, m=w["m"], sys=sysd, shared=w["shared"], params=p, nthreads=cores)
+        _, _, _, st = oracle_solve_batch(o, w, x0, sysd, params=p, nthreads=cores)
         elapsed += time.perf_counter() - t0
         conv += int((st == 0).sum())
         reps += 1
@@ -162,7 +174,7 @@ def flops_per_system(w, sample=4096):
     x0 = np.ascontiguousarray(w["x0"][:, idx])
     sysd = None if w["args"] is None else np.ascontiguousarray(w["args"][:, idx])
     o.flops_reset()
-    o.solve_batch(w["solver"], w["fcn"], x0, m=w["m"], sys=sysd, shared=w["shared"], params=oracle_params(o, w))
+    oracle_solve_batch(o, w, x0, sysd, params=oracle_params(o, w))
     return o.flops_total() / float(idx.size)
 
 
@@ -182,13 +194,13 @@ def run_reference(args):
     p = oracle_params(o, w)
     cores = os.cpu_count() or 1
     # bounded sample per step so that K steps finish within minutes
-    nsub = B if args.workload in ("C1", "C2", "C3", "LM4") else min(B, 256)
+    nsub = B if args.workload in ("C1", "C2", "C3", "LM4", "CLS1", "CLS2") else min(B, 256)
     x0 = np.ascontiguousarray(w["x0"][:, :nsub]); sysd = None if w["args"] is None else np.ascontiguousarray(w["args"][:, :nsub])
     for _ in range(args.warmup):
-        o.solve_batch(w["solver"], w["fcn"], x0, m=w["m"], sys=sysd, shared=w["shared"], params=p, nthreads=cores)
+        oracle_solve_batch(o, w, x0, sysd, params=p, nthreads=cores)
     t0 = time.perf_counter(); conv = 0
     for _ in range(args.steps):
-        _, _, _, st = o.solve_batch(w["solver"], w["fcn"], x0, m=w["m"], sys=sysd, shared=w["shared"], params=p, nthreads=cores)
+        _, _, _, st = oracle_solve_batch(o, w, x0, sysd, params=p, nthreads=cores)
         conv += int((st == 0).sum())
     dt = time.perf_counter() - t0
     val = conv / dt
@@ -210,7 +222,8 @@ def run_reference(args):
 # engine arm
 # ---------------------------------------------------------------------------------------------
 def make_solver(nb, w, eng):
-    s = {"least_squares": nb.least_squares_solver, "newton": nb.newton_solver, "quasi_newton": nb.quasi_newton_solver}[w["solver"]](engine=eng)
+    s = {"least_squares": nb.least_squares_solver, "newton": nb.newton_solver, "quasi_newton": nb.quasi_newton_solver,
+         "constrained_least_squares": nb.constrained_least_squares_solver}[w["solver"]](engine=eng)
     for k, v in w["settings"].items():
         getattr(s, k)(v)
     return s
@@ -448,8 +461,9 @@ def run_engine(args):
             traffic = None
     roofline = {
         "bound": "fp64", "kernel": {"C1": "tps_solve_kernel<LsqPolyFit, LM>", "C2": "tps_solve_kernel<Misc2Fcn, Broyden>",
-                                    "C3": "tps_newton_refill_kernel<PowellBadlyScaled>", "C4": "coop_lm_kernel<Rational78, 16>",
-                                    "C5": "coop_broyden_kernel<ExtRosenbrock, 64>", "LM4": "coop_lm_kernel<ExpDecay4, 4>"}[w["name"]],
+                                    "C3": "tps_newton_refill_kernel<PowellBadlyScaled>", "C4": "wlm_kernel<Rational78, 16>",
+                                    "C5": "coop_broyden_kernel<ExtRosenbrock, 64>", "LM4": "coop_lm_kernel<ExpDecay4, 4>",
+                                    "CLS1": "tps_cls_kernel<LsqPolyFit>", "CLS2": "tps_cls_kernel<Misc2Fcn>"}[w["name"]],
         "achieved": achieved_tf, "peak": peak["dfma_tflops"], "unit": "TFLOP/s", "frac": achieved_tf / peak["dfma_tflops"],
         "peak_source": "DFMA micro-kernel measured on this GPU at run time (MEASURED_PEAKS.json has no FP64 entry)",
         "peak_no_fma": peak["dadd_dmul_tflops"], "frac_of_no_fma_peak": achieved_tf / peak["dadd_dmul_tflops"],
@@ -463,7 +477,7 @@ def run_engine(args):
 
     extras = {}
     if not args.no_extras and world == 1:
-        for name in ("C1", "C3", "C5", "LM4"):
+        for name in ("C1", "C3", "C5", "LM4", "CLS1", "CLS2"):
             if name == args.workload:
                 continue
             try:

@@ -16,6 +16,7 @@ module nonlin_batch
     private
     public :: nlb_engine, batch_vecfcn_helper, batch_iteration_behavior
     public :: batch_least_squares_solver, batch_newton_solver, batch_quasi_newton_solver, batch_line_search
+    public :: batch_constrained_least_squares_solver
     public :: NLB_OK, NL_NO_ERROR, NL_CONVERGENCE_ERROR, NL_DIVERGENT_BEHAVIOR_ERROR, &
         NL_SPURIOUS_CONVERGENCE_ERROR
 
@@ -32,6 +33,12 @@ module nonlin_batch
         integer(c_int32_t) :: jacobian_interval, use_line_search, ls_max_fcn_evals
         real(c_double) :: ls_alpha, ls_factor
         integer(c_int32_t) :: use_analytic_jacobian, max_iter_guard
+    end type
+
+    !> struct nlb_constrained_options (lower / upper: c_loc of n host doubles, or c_null_ptr)
+    type, bind(C) :: nlb_constrained_options
+        real(c_double) :: trust_region_radius, step_scaling_factor
+        type(c_ptr) :: lower, upper
     end type
 
     !> struct nlb_iteration_behavior == iteration_behavior (nonlin_types.f90:8-29) with C ints for the logicals
@@ -63,6 +70,16 @@ module nonlin_batch
             import :: c_ptr, c_int, c_int64_t, nlb_params
             type(c_ptr), value :: handle
             type(nlb_params), intent(in) :: params
+            integer(c_int), value :: fcn_id, m, n
+            integer(c_int64_t), value :: b
+            type(c_ptr), value :: x, fvec, sys, shared, ib, status, stream
+        end function
+        integer(c_int) function nlb_constrained_least_squares_solve_batch(handle, params, options, fcn_id, b, m, n, &
+                x, fvec, sys, shared, ib, status, stream) bind(C, name = "nlb_constrained_least_squares_solve_batch")
+            import :: c_ptr, c_int, c_int64_t, nlb_params, nlb_constrained_options
+            type(c_ptr), value :: handle
+            type(nlb_params), intent(in) :: params
+            type(nlb_constrained_options), intent(in) :: options
             integer(c_int), value :: fcn_id, m, n
             integer(c_int64_t), value :: b
             type(c_ptr), value :: x, fvec, sys, shared, ib, status, stream
@@ -155,6 +172,20 @@ module nonlin_batch
     contains
         procedure, public :: set_step_scaling_factor => bls_set_factor
         procedure, public :: solve_batch => lss_solve_batch
+    end type
+
+    !> constrained_least_squares_solver (nonlin_least_squares.f90:34-75): limits, radius, step scaling
+    type, extends(batch_equation_solver) :: batch_constrained_least_squares_solver
+        real(real64), private, allocatable, dimension(:) :: m_upper
+        real(real64), private, allocatable, dimension(:) :: m_lower
+        real(real64), private :: m_delta = 1.0d0
+        real(real64), private :: m_scaling = 1.0d0
+    contains
+        procedure, public :: set_upper_limits => bcls_set_upper
+        procedure, public :: set_lower_limits => bcls_set_lower
+        procedure, public :: set_trust_region_radius => bcls_set_radius
+        procedure, public :: set_step_scaling_factor => bcls_set_factor
+        procedure, public :: solve_batch => cls_solve_batch
     end type
 
     type, abstract, extends(batch_equation_solver) :: batch_line_search_solver
@@ -346,6 +377,65 @@ contains
         if (present(args)) pa = c_loc(args)
         if (present(shared)) ps = c_loc(shared)
         ierr = nlb_least_squares_solve_batch(eng%handle, p, fcn%m_fcn, int(size(x, 1), c_int64_t), &
+            int(fcn%m_nfcn, c_int), int(fcn%m_nvar, c_int), c_loc(x), c_loc(fvec), pa, ps, c_loc(ib), &
+            c_loc(status), c_null_ptr)
+    end subroutine
+
+    subroutine bcls_set_upper(this, x)
+        class(batch_constrained_least_squares_solver), intent(inout) :: this
+        real(real64), intent(in), dimension(:) :: x
+        this%m_upper = x
+    end subroutine
+
+    subroutine bcls_set_lower(this, x)
+        class(batch_constrained_least_squares_solver), intent(inout) :: this
+        real(real64), intent(in), dimension(:) :: x
+        this%m_lower = x
+    end subroutine
+
+    subroutine bcls_set_radius(this, x)
+        class(batch_constrained_least_squares_solver), intent(inout) :: this
+        real(real64), intent(in) :: x
+        this%m_delta = merge(1.0d0, x, x <= 0.0d0)
+    end subroutine
+
+    subroutine bcls_set_factor(this, x)
+        class(batch_constrained_least_squares_solver), intent(inout) :: this
+        real(real64), intent(in) :: x
+        this%m_scaling = merge(1.0d0, x, x <= 0.0d0)
+    end subroutine
+
+    !> Batch analogue of constrained_least_squares_solver%solve; arguments as lss_solve_batch.  The limits
+    !! apply to every system of the batch; limit arrays whose length is not n are ignored, as cls_solve
+    !! replaces them by -huge / +huge.
+    subroutine cls_solve_batch(this, eng, fcn, x, fvec, ib, status, ierr, args, shared)
+        class(batch_constrained_least_squares_solver), intent(in), target :: this
+        type(nlb_engine), intent(in) :: eng
+        class(batch_vecfcn_helper), intent(in) :: fcn
+        real(real64), intent(inout), dimension(:,:), contiguous, target :: x
+        real(real64), intent(out), dimension(:,:), contiguous, target :: fvec
+        type(batch_iteration_behavior), intent(out), dimension(:), target :: ib
+        integer(int32), intent(out), dimension(:), target :: status
+        integer, intent(out) :: ierr
+        real(real64), intent(in), dimension(:,:), contiguous, target, optional :: args
+        real(real64), intent(in), dimension(:), contiguous, target, optional :: shared
+        type(nlb_params) :: p
+        type(nlb_constrained_options) :: o
+        type(c_ptr) :: pa, ps
+        p = this%base_params(fcn)
+        o%trust_region_radius = this%m_delta
+        o%step_scaling_factor = this%m_scaling
+        o%lower = c_null_ptr; o%upper = c_null_ptr
+        if (allocated(this%m_lower)) then
+            if (size(this%m_lower) == fcn%m_nvar) o%lower = c_loc(this%m_lower)
+        end if
+        if (allocated(this%m_upper)) then
+            if (size(this%m_upper) == fcn%m_nvar) o%upper = c_loc(this%m_upper)
+        end if
+        pa = c_null_ptr; ps = c_null_ptr
+        if (present(args)) pa = c_loc(args)
+        if (present(shared)) ps = c_loc(shared)
+        ierr = nlb_constrained_least_squares_solve_batch(eng%handle, p, o, fcn%m_fcn, int(size(x, 1), c_int64_t), &
             int(fcn%m_nfcn, c_int), int(fcn%m_nvar, c_int), c_loc(x), c_loc(fvec), pa, ps, c_loc(ib), &
             c_loc(status), c_null_ptr)
     end subroutine

@@ -9,6 +9,7 @@
 #pragma once
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "../../include/nonlin_batch.h"
 
@@ -116,6 +117,48 @@ protected:
         return nlb_least_squares_solve_batch(h, &p, f.id(), B, f.get_equation_count(), f.get_variable_count(), x, fvec,
                                              args, f.shared(), ib, status, stream);
     }
+};
+
+// reference src/nonlin_least_squares.f90:34-48
+class constrained_equation_solver : public equation_solver {
+public:
+    std::vector<double> get_upper_limits() const { return upper_; }
+    void set_upper_limits(const std::vector<double>& x) { upper_ = x; }
+    std::vector<double> get_lower_limits() const { return lower_; }
+    void set_lower_limits(const std::vector<double>& x) { lower_ = x; }
+    // ces_apply_limits (:858-883) on one host vector: lower limits first, then upper
+    void apply_limits(std::vector<double>& x) const {
+        for (size_t i = 0; i < x.size() && i < lower_.size(); ++i) if (x[i] < lower_[i]) x[i] = lower_[i];
+        for (size_t i = 0; i < x.size() && i < upper_.size(); ++i) if (x[i] > upper_[i]) x[i] = upper_[i];
+    }
+protected:
+    std::vector<double> lower_, upper_;
+};
+
+// reference src/nonlin_least_squares.f90:50-75
+class constrained_least_squares_solver : public constrained_equation_solver {
+public:
+    double get_trust_region_radius() const { return delta_; }
+    void set_trust_region_radius(double x) { delta_ = x <= 0.0 ? 1.0 : x; }
+    double get_step_scaling_factor() const { return scaling_; }
+    void set_step_scaling_factor(double x) { scaling_ = x <= 0.0 ? 1.0 : x; }
+protected:
+    int launch(nlb_handle* h, const nlb_params& p, const vecfcn_helper& f, int64_t B, double* x, double* fvec,
+               iteration_behavior* ib, int32_t* status, const double* args, void* stream) override {
+        nlb_constrained_options o;
+        nlb_constrained_options_default(&o);
+        o.trust_region_radius = delta_;
+        o.step_scaling_factor = scaling_;
+        // limit arrays of the wrong length are replaced by -huge / +huge (cls_solve :1014-1024)
+        const size_t n = (size_t)f.get_variable_count();
+        if (lower_.size() == n) o.lower = lower_.data();
+        if (upper_.size() == n) o.upper = upper_.data();
+        return nlb_constrained_least_squares_solve_batch(h, &p, &o, f.id(), B, f.get_equation_count(),
+                                                         f.get_variable_count(), x, fvec, args, f.shared(), ib, status,
+                                                         stream);
+    }
+private:
+    double delta_ = 1.0, scaling_ = 1.0;
 };
 
 // reference src/nonlin_solve.f90:20-41

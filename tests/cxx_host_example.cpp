@@ -27,6 +27,22 @@ int main() {
                 return 1;
             }
         }
+        // test_constrained_least_squares_bounds (tests/nonlin_test_solve.f90:1186): start (1, 1) outside the box
+        // [4, 5.6] x [2, 3.6]; the solution must be feasible and is the root (5, 3)
+        nonlin::constrained_least_squares_solver csolver;
+        csolver.set_lower_limits({4.0, 2.0});
+        csolver.set_upper_limits({5.6, 3.6});
+        std::vector<double> xc(2 * B, 1.0), fc(2 * B);
+        std::vector<nonlin::iteration_behavior> ibc(B);
+        std::vector<int32_t> statusc(B);
+        csolver.solve(eng, obj, B, xc.data(), fc.data(), ibc.data(), statusc.data());
+        for (int64_t b = 0; b < B; ++b) {
+            const double d0 = xc[b] - 5.0, d1 = xc[B + b] - 3.0;
+            if (statusc[b] != 0 || ibc[b].converge_on_fcn == 0 || d0 > 1e-6 || d0 < -1e-6 || d1 > 1e-6 || d1 < -1e-6) {
+                std::printf("FAIL (constrained) at %lld\n", (long long)b);
+                return 1;
+            }
+        }
         std::printf("Solution: (%.5f, %.5f)\nResidual: (%.3e, %.3e)\nIterations: %d\nFunction Evaluations: %d\nJacobian Evaluations: %d\n",
                     x[0], x[B], f[0], f[B], ib[0].iter_count, ib[0].fcn_count, ib[0].jacobian_count);
     } catch (const nonlin::error& e) {

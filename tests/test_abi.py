@@ -153,7 +153,8 @@ def test_fortran_binding_declares_every_solver_entry_point():
     src = open(os.path.join(ROOT, "fortran", "nonlin_batch.f90")).read()
     names = set(re.findall(r'bind\(C, name = "(nlb_\w+)"\)', src))
     assert {"nlb_create", "nlb_destroy", "nlb_least_squares_solve_batch", "nlb_newton_solve_batch",
-            "nlb_quasi_newton_solve_batch", "nlb_jacobian_batch", "nlb_reduce_stats"} <= names
+            "nlb_quasi_newton_solve_batch", "nlb_constrained_least_squares_solve_batch", "nlb_jacobian_batch",
+            "nlb_reduce_stats"} <= names
     lib = C.CDLL(_lib.LIB_PATH)
     for n in names:
         assert hasattr(lib, n)

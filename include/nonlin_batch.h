@@ -168,6 +168,26 @@ int nlb_constrained_least_squares_solve_batch(nlb_handle* handle, const nlb_para
                                               int n, double* x, double* fvec, const double* sys, const double* shared,
                                               nlb_iteration_behavior* ib, int32_t* status, void* stream);
 
+/* polynomial%fit  (poly_fit, src/nonlin_polynomials.f90:146-199) and, with thru_zero != 0, polynomial%fit_thru_zero
+ * (poly_fit_thru_zero, :202-253) over B data sets of npts points each: the least-squares polynomial of the given
+ * order through (x, y), solved as the reference does (Vandermonde matrix, linalg solve_least_squares = LAPACK DGELS).
+ *   x       abscissae: npts doubles shared by every data set (x_is_shared != 0) or x[i*B + b]
+ *   y       ordinates y[i*B + b]; NOT overwritten (the reference's y is intent(inout) scratch)
+ *   coeffs  out, coeffs[k*B + b] = c_k of data set b, k = 0..order (c0 first, as polynomial%get(k+1));
+ *           c0 = 0 for thru_zero
+ *   status  out (may be NULL): 0, or NLB_LA_INVALID_OPERATION_ERROR where the matrix is exactly rank deficient
+ *           (linalg reports that instead of returning coefficients)
+ * `order >= npts` or `order < 1` is the reference's `error stop 4` (:166-169): NLB_ERR_SIZE.  At most 8 fitted
+ * coefficients (order <= 7, or <= 8 through zero); more returns NLB_ERR_UNSUPPORTED. */
+#define NLB_LA_INVALID_OPERATION_ERROR 107
+int nlb_polynomial_fit_batch(nlb_handle* handle, int64_t B, int npts, int order, int thru_zero, int x_is_shared,
+                             const double* x, const double* y, double* coeffs, int32_t* status, void* stream);
+
+/* polynomial%evaluate  (poly_eval_double, src/nonlin_polynomials.f90:256-283) for B polynomials at npts points:
+ * y[i*B + b] = c_order x^order + ... + c_0, Horner from the highest coefficient.  order 0..8. */
+int nlb_polynomial_evaluate_batch(nlb_handle* handle, int64_t B, int order, int npts, int x_is_shared,
+                                  const double* coeffs, const double* x, double* y, void* stream);
+
 /* vecfcn_helper%fcn  (vfh_fcn, src/nonlin_multi_eqn_mult_var.f90:178-195) over B points. */
 int nlb_vecfcn_eval_batch(nlb_handle* handle, int fcn_id, int64_t B, int m, int n, const double* x, double* fvec,
                           const double* sys, const double* shared, void* stream);

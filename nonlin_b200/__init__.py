@@ -7,6 +7,7 @@ Importing this package loads the shared library and fails loudly if it is missin
 """
 from ._lib import (  # noqa: F401
     IB_DTYPE,
+    LA_INVALID_OPERATION_ERROR,
     NL_CONVERGENCE_ERROR,
     NL_DIVERGENT_BEHAVIOR_ERROR,
     NL_INVALID_INPUT_ERROR,
@@ -35,6 +36,7 @@ from .api import (  # noqa: F401
     line_search,
     line_search_solver,
     newton_solver,
+    polynomial,
     quasi_newton_solver,
     vecfcn_helper,
     vecfcn_names,

@@ -30,6 +30,8 @@ NL_SPURIOUS_CONVERGENCE_ERROR = 207
 NL_TOLERANCE_TOO_SMALL_ERROR = 208
 NL_UNDEFINED_FUNCTION_ERROR = 211
 NL_UNDERDEFINED_PROBLEM_ERROR = 212
+LA_INVALID_OPERATION_ERROR = 107   # linalg: rank-deficient solve_least_squares (polynomial fit)
+NL_LA_INVALID_OPERATION_ERROR = LA_INVALID_OPERATION_ERROR   # header name: NLB_LA_INVALID_OPERATION_ERROR
 
 NLB_STAT_NAMES = ["systems", "converged", "converged_fcn", "converged_chng", "converged_zero_diff", "failed",
                   "sum_iter", "sum_fcn", "sum_jac", "max_iter"]
@@ -41,6 +43,7 @@ EXPORTS = [
     "nlb_least_squares_solve_batch", "nlb_newton_solve_batch", "nlb_quasi_newton_solve_batch",
     "nlb_vecfcn_eval_batch", "nlb_jacobian_batch", "nlb_reduce_stats", "nlb_measure_fp64_peak",
     "nlb_measure_fp64_latency", "nlb_constrained_options_default", "nlb_constrained_least_squares_solve_batch",
+    "nlb_polynomial_fit_batch", "nlb_polynomial_evaluate_batch",
 ]
 
 
@@ -111,6 +114,8 @@ def load():
     lib.nlb_constrained_options_default.restype = None
     lib.nlb_constrained_least_squares_solve_batch.argtypes = (
         [vp, C.POINTER(nlb_params), C.POINTER(nlb_constrained_options)] + solve_args[2:])
+    lib.nlb_polynomial_fit_batch.argtypes = [vp, i64, i32, i32, i32, i32, vp, vp, vp, vp, vp]
+    lib.nlb_polynomial_evaluate_batch.argtypes = [vp, i64, i32, i32, i32, vp, vp, vp, vp]
     lib.nlb_vecfcn_eval_batch.argtypes = [vp, i32, i64, i32, i32, vp, vp, vp, vp, vp]
     lib.nlb_jacobian_batch.argtypes = [vp, C.POINTER(nlb_params), i32, i64, i32, i32, vp, vp, vp, vp, vp]
     lib.nlb_reduce_stats.argtypes = [vp, i64, vp, vp, vp, vp]

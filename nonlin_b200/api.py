@@ -271,12 +271,12 @@ class vecfcn_helper:
         return jac
 
 
-def _empty_like(a, shape):
+def _empty_like(a, shape, dtype="float64"):
     if _is_torch(a):
         import torch
 
-        return torch.empty(shape, dtype=torch.float64, device=a.device)
-    return np.empty(shape, dtype=np.float64)
+        return torch.empty(shape, dtype=getattr(torch, dtype), device=a.device)
+    return np.empty(shape, dtype=dtype)
 
 
 class line_search:
@@ -572,6 +572,83 @@ class newton_solver(line_search_solver):
     """Newton's method with LU (reference src/nonlin_solve.f90:60-67, ns_solve :452-638)."""
 
     _entry = "nlb_newton_solve_batch"
+
+
+class polynomial:
+    """A batch of B polynomials of one order, c0 + c1 x + ... (reference `polynomial`,
+    src/nonlin_polynomials.f90:20-71): `fit`, `fit_thru_zero`, `evaluate`, `order`, `get`, `get_all`, `set`,
+    `initialize`.  Coefficients are an (order + 1, B) array, data-set index fastest; `get(i)` / `set(i, v)` use the
+    reference's 1-based index (get(1) = c0).  Roots, companion matrix and polynomial arithmetic are host-side
+    single-polynomial operations outside the batch path and are not mirrored."""
+
+    def __init__(self, order=None, B=1, engine=None):
+        self._engine = engine
+        self._c = None
+        if order is not None:
+            self.initialize(order, B)
+
+    def initialize(self, order, B=1):
+        """`call p%initialize(order)` (init_poly :77-103) or, with an array, `p%initialize(c)` (init_poly_coeffs :106-128)."""
+        if np.ndim(order) > 0:
+            c = np.array(order, dtype=np.float64)
+            self._c = np.ascontiguousarray(c.reshape(c.shape[0], -1))
+            return
+        if order < 0:
+            raise NonlinError(_lib.NLB_ERR_INVALID_ARGUMENT, "order must be >= 0")   # reference: error stop
+        self._c = np.zeros((int(order) + 1, int(B)))
+
+    def order(self):
+        return -1 if self._c is None else int(self._c.shape[0]) - 1
+
+    def get(self, i):
+        return self._c[i - 1]
+
+    def get_all(self):
+        return self._c
+
+    def set(self, i, v):
+        self._c[i - 1] = v
+
+    def _fit(self, x, y, order, thru_zero, status, stream):
+        if y.ndim != 2:
+            raise NonlinError(_lib.NLB_ERR_SIZE, "y must be (npts, B)")
+        npts, B = y.shape
+        shared = x.ndim == 1
+        _check_f64("y", y, (npts, B))
+        _check_f64("x", x, (npts,) if shared else (npts, B))            # size(y) /= size(x): error stop 3
+        c = _empty_like(y, (int(order) + 1, B))
+        if status is None:
+            status = _empty_like(y, (B,), dtype="int32")
+        eng = self._engine or default_engine(_device_of(x, y) or 0)
+        eng.check(_LIB.nlb_polynomial_fit_batch(eng._h, B, npts, int(order), int(thru_zero), int(shared), _ptr(x), _ptr(y),
+                                                _ptr(c), _ptr(status),
+                                                C.c_void_p(stream) if stream is not None else _stream_of(x, y)))
+        self._c = c
+        return status
+
+    def fit(self, x, y, order, status=None, stream=None):
+        """`call p%fit(x, y, order)` for B data sets: y (npts, B), x (npts,) shared or (npts, B).  Returns the
+        per-set status (0, or LA_INVALID_OPERATION_ERROR for an exactly rank-deficient set).  y is not overwritten."""
+        return self._fit(x, y, order, False, status, stream)
+
+    def fit_thru_zero(self, x, y, order, status=None, stream=None):
+        """`call p%fit_thru_zero(x, y, order)`: same with c0 forced to 0 (poly_fit_thru_zero :202-253)."""
+        return self._fit(x, y, order, True, status, stream)
+
+    def evaluate(self, x, stream=None):
+        """`p%evaluate(x)`: (npts, B) values of the B polynomials at x (npts,) or (npts, B) (poly_eval_double :256-283)."""
+        if self._c is None:
+            raise NonlinError(_lib.NLB_ERR_INVALID_ARGUMENT, "polynomial is not initialised")
+        B = self._c.shape[1]
+        shared = x.ndim == 1
+        npts = x.shape[0]
+        _check_f64("x", x, (npts,) if shared else (npts, B))
+        yv = _empty_like(self._c, (npts, B))
+        eng = self._engine or default_engine(_device_of(x, self._c) or 0)
+        eng.check(_LIB.nlb_polynomial_evaluate_batch(eng._h, B, self.order(), npts, int(shared), _ptr(self._c), _ptr(x),
+                                                     _ptr(yv),
+                                                     C.c_void_p(stream) if stream is not None else _stream_of(x, self._c)))
+        return yv
 
 
 def vecfcn_names():

@@ -9,7 +9,10 @@
 #include <mutex>
 #include <string>
 
+#include <cstdlib>
+
 #include "coop_kernels.cuh"
+#include "polyfit.cuh"
 #include "tps_cls.cuh"
 #include "tps_lm.cuh"
 #include "tps_newton_broyden.cuh"
@@ -32,6 +35,8 @@ struct nlb_handle {
     unsigned long long* dcursor = nullptr;         // work-queue cursors of the persistent kernels (16 slots)
     unsigned cursor_next = 0;
     int num_sms = 0;
+    void* dwork = nullptr;                         // grow-only workspace of the polynomial-fit kernel
+    size_t dwork_cap = 0;
     cudaStream_t pipe[2] = {nullptr, nullptr};   // copy/compute pipeline for host-resident batches
     cudaEvent_t ev_in = nullptr, ev_out[2] = {nullptr, nullptr};
     std::mutex mu;
@@ -581,6 +586,7 @@ int nlb_destroy(nlb_handle* h) {
     cudaSetDevice(h->device);
     for (int i = 0; i < nlb_handle::NSLOT; ++i)
         if (h->dbuf[i]) cudaFree(h->dbuf[i]);
+    if (h->dwork) cudaFree(h->dwork);
     if (h->dstats) cudaFree(h->dstats);
     if (h->dcursor) cudaFree(h->dcursor);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -683,6 +689,92 @@ int nlb_constrained_least_squares_solve_batch(nlb_handle* h, const nlb_params* p
         o.xu[i] = (options->upper && i < nv) ? options->upper[i] : huge;
     }
     return solve_batch(h, SOLVER_CLS, params, fcn_id, B, m, n, x, fvec, sys, shared, ib, status, stream, &o);
+}
+
+int nlb_polynomial_fit_batch(nlb_handle* h, int64_t B, int npts, int order, int thru_zero, int x_is_shared,
+                             const double* x, const double* y, double* coeffs, int32_t* status, void* stream) {
+    if (!h) return NLB_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(h->mu);
+    if (B < 0 || (B > 0 && (!x || !y || !coeffs))) return set_err(h, NLB_ERR_INVALID_ARGUMENT, "null argument or B < 0");
+    // poly_fit: `order >= n .or. order < 1` -> error stop 4 (src/nonlin_polynomials.f90:166-169, 224-227)
+    if (npts <= 0 || order < 1 || order >= npts) return set_err(h, NLB_ERR_SIZE, "need 1 <= order < npts");
+    const int nc = thru_zero ? order : order + 1;
+    if (nc > POLY_MAX_COLS) return set_err(h, NLB_ERR_UNSUPPORTED, "polynomial fit: at most 8 fitted coefficients");
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    if (B == 0) return NLB_OK;
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    Staged ax, ay, ac, ast;
+    const size_t xbytes = sizeof(double) * (size_t)npts * (x_is_shared ? 1 : (size_t)B);
+    if ((rc = stage_in(h, x_is_shared ? 3 : 0, x, xbytes, true, s, &ax))) return rc;
+    if ((rc = stage_in(h, 1, y, sizeof(double) * (size_t)npts * B, true, s, &ay))) return rc;
+    if ((rc = stage_in(h, 2, coeffs, sizeof(double) * (size_t)(order + 1) * B, false, s, &ac))) return rc;
+    if ((rc = stage_in(h, 5, status, sizeof(int32_t) * (size_t)B, false, s, &ast))) return rc;
+    // persistent grid: enough threads to fill the GPU, few enough that the live workspace stays near L2
+    static int threads_per_sm = 0;
+    if (threads_per_sm == 0) {
+        const char* e = std::getenv("NLB_POLYFIT_THREADS_PER_SM");   // tuning knob, multiple of 128
+        threads_per_sm = e ? std::atoi(e) : 1024;
+        if (threads_per_sm < 128) threads_per_sm = 128;
+    }
+    const size_t per_thread = sizeof(double) * (size_t)npts * (size_t)(nc + 1);
+    long long T = (long long)h->num_sms * threads_per_sm;
+    const long long need = ((B + 127) / 128) * 128;
+    if (T > need) T = need;
+    const size_t budget = (size_t)2 << 30;
+    while (T > 128 && (size_t)T * per_thread > budget) T -= 128;
+    if ((size_t)T * per_thread > budget) return set_err(h, NLB_ERR_UNSUPPORTED, "polynomial fit: npts too large");
+    if (h->dwork_cap < (size_t)T * per_thread) {
+        NLB_CUDA(h, cudaStreamSynchronize(s));
+        if (h->dwork) NLB_CUDA(h, cudaFree(h->dwork));
+        h->dwork = nullptr;
+        h->dwork_cap = 0;
+        NLB_CUDA(h, cudaMalloc(&h->dwork, (size_t)T * per_thread));
+        h->dwork_cap = (size_t)T * per_thread;
+    }
+    const unsigned grid = (unsigned)(T / 128);
+    switch (nc) {
+#define X(NC)                                                                                                  \
+    case NC:                                                                                                   \
+        polyfit_kernel<NC><<<grid, 128, 0, s>>>(B, npts, thru_zero != 0, x_is_shared != 0, (const double*)ax.dev, \
+                                                (const double*)ay.dev, (double*)ac.dev, (int32_t*)ast.dev,      \
+                                                (double*)h->dwork);                                            \
+        break;
+        X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
+#undef X
+    }
+    ++h->launches;
+    NLB_CUDA(h, cudaGetLastError());
+    if ((rc = stage_out(h, ac, s))) return rc;
+    if ((rc = stage_out(h, ast, s))) return rc;
+    if (ax.staged || ay.staged || ac.staged || ast.staged) NLB_CUDA(h, cudaStreamSynchronize(s));
+    return NLB_OK;
+}
+
+int nlb_polynomial_evaluate_batch(nlb_handle* h, int64_t B, int order, int npts, int x_is_shared,
+                                  const double* coeffs, const double* x, double* y, void* stream) {
+    if (!h) return NLB_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(h->mu);
+    if (B < 0 || npts < 0 || (B > 0 && npts > 0 && (!x || !y || !coeffs)))
+        return set_err(h, NLB_ERR_INVALID_ARGUMENT, "null argument or negative size");
+    if (order < 0 || order > POLY_MAX_COLS) return set_err(h, NLB_ERR_UNSUPPORTED, "polynomial evaluate: order 0..8");
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    if (B == 0 || npts == 0) return NLB_OK;
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    Staged ax, ay, ac;
+    const size_t xbytes = sizeof(double) * (size_t)npts * (x_is_shared ? 1 : (size_t)B);
+    if ((rc = stage_in(h, x_is_shared ? 3 : 0, x, xbytes, true, s, &ax))) return rc;
+    if ((rc = stage_in(h, 1, y, sizeof(double) * (size_t)npts * B, false, s, &ay))) return rc;
+    if ((rc = stage_in(h, 2, coeffs, sizeof(double) * (size_t)(order + 1) * B, true, s, &ac))) return rc;
+    const unsigned grid = (unsigned)((B + 127) / 128);
+    polyval_kernel<<<grid, 128, 0, s>>>(B, order, npts, x_is_shared != 0, (const double*)ac.dev, (const double*)ax.dev,
+                                        (double*)ay.dev);
+    ++h->launches;
+    NLB_CUDA(h, cudaGetLastError());
+    if ((rc = stage_out(h, ay, s))) return rc;
+    if (ax.staged || ay.staged || ac.staged) NLB_CUDA(h, cudaStreamSynchronize(s));
+    return NLB_OK;
 }
 
 int nlb_vecfcn_eval_batch(nlb_handle* h, int fcn_id, int64_t B, int m, int n, const double* x, double* fvec,

@@ -88,6 +88,8 @@ class Oracle:
         lib.nlo_jacobian.restype = C.c_int
         lib.nlo_dgesv.restype = C.c_int
         lib.nlo_cls_solve.restype = C.c_int
+        lib.nlo_polyfit_batch.restype = C.c_int
+        lib.nlo_polyval_batch.restype = C.c_int
         lib.nlo_cls_solve_batch.restype = C.c_int
 
     # -- registry -----------------------------------------------------------------------
@@ -229,6 +231,33 @@ class Oracle:
         if rc:
             raise RuntimeError("nlo_cls_solve_batch -> %d" % rc)
         return x, f, ib, status
+
+    def polyfit_batch(self, x, y, order, thru_zero=False, nthreads=0):
+        """polynomial%fit over B data sets. x: (npts,) shared or (npts, B); y: (npts, B).
+        Returns (coeffs (order+1, B), status (B,))."""
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        npts, B = y.shape
+        shared = x.ndim == 1
+        if x.shape[0] != npts or (not shared and x.shape != y.shape):
+            raise ValueError("x / y shapes")
+        c = np.zeros((order + 1, B))
+        status = np.zeros(B, dtype=np.int32)
+        rc = self.lib.nlo_polyfit_batch(C.c_long(B), npts, int(order), int(bool(thru_zero)), int(shared), self._ptr(x),
+                                        self._ptr(y), self._ptr(c), self._ptr(status), int(nthreads))
+        if rc:
+            raise RuntimeError("nlo_polyfit_batch -> %d" % rc)
+        return c, status
+
+    def polyval_batch(self, coeffs, x):
+        """polynomial%evaluate: coeffs (order+1, B), x (npts,) or (npts, B) -> (npts, B)."""
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        B = coeffs.shape[1]
+        y = np.zeros((x.shape[0], B))
+        self.lib.nlo_polyval_batch(C.c_long(B), coeffs.shape[0] - 1, x.shape[0], int(x.ndim == 1), self._ptr(coeffs),
+                                   self._ptr(x), self._ptr(y))
+        return y
 
     def solve_batch(self, solver, fcn, x0, m=0, sys=None, shared=None, params=None, nthreads=0):
         """x0: (n, B) SoA. Returns (x (n,B), fvec (m,B), ib (B,) structured, status (B,))."""

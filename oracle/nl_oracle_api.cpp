@@ -16,6 +16,7 @@
 #endif
 
 #include "nl_lapack.h"
+#include "nl_polynomial.h"
 #include "nl_solvers.h"
 
 namespace nlo {
@@ -208,6 +209,54 @@ int nlo_cls_solve_batch(int fcn_id, long B, int m, int n, const Params* prm, con
 #ifdef NL_COUNT_FLOPS
         g_flops_total += g_flops;
 #endif
+    }
+    return 0;
+}
+
+// polynomial%fit / fit_thru_zero over B data sets.  x: npts (x_is_shared) or npts x B; y: npts x B (not modified
+// here: each fit works on a copy, the reference overwrites its y); coeffs: (order + 1) x B, c0 first.
+int nlo_polyfit_batch(long B, int npts, int order, int thru_zero, int x_is_shared, const double* x, const double* y,
+                      double* coeffs, int32_t* status, int nthreads) {
+    if (order < 1 || order >= npts || order + 1 > 64) return NL_INVALID_INPUT_ERROR;   // error stop 4 (:160-163)
+    const int ncols = thru_zero ? order : order + 1;
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+    nthreads = 1;
+#endif
+#pragma omp parallel num_threads(nthreads)
+    {
+        std::vector<real> xl(npts), yl(npts), a((size_t)npts * ncols), c(order + 1);
+#ifdef NL_COUNT_FLOPS
+        g_flops = 0;
+#endif
+#pragma omp for schedule(dynamic, 64)
+        for (long b = 0; b < B; ++b) {
+            for (int i = 0; i < npts; ++i) {
+                xl[i] = x_is_shared ? R(x)[i] : R(x)[(long)i * B + b];
+                yl[i] = R(y)[(long)i * B + b];
+            }
+            int st = thru_zero ? poly_fit_thru_zero(npts, order, xl.data(), yl.data(), c.data(), a.data())
+                               : poly_fit(npts, order, xl.data(), yl.data(), c.data(), a.data());
+            for (int j = 0; j <= order; ++j) R(coeffs)[(long)j * B + b] = c[j];
+            if (status) status[b] = st;
+        }
+#ifdef NL_COUNT_FLOPS
+        g_flops_total += g_flops;
+#endif
+    }
+    return 0;
+}
+
+// polynomial%evaluate: y[i*B + b] = p_b(x_i)
+int nlo_polyval_batch(long B, int order, int npts, int x_is_shared, const double* coeffs, const double* x, double* y) {
+    std::vector<real> c(order + 1);
+    for (long b = 0; b < B; ++b) {
+        for (int j = 0; j <= order; ++j) c[j] = R(coeffs)[(long)j * B + b];
+        for (int i = 0; i < npts; ++i) {
+            real xv = x_is_shared ? R(x)[i] : R(x)[(long)i * B + b];
+            R(y)[(long)i * B + b] = poly_eval(order, c.data(), xv);
+        }
     }
     return 0;
 }

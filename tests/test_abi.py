@@ -32,7 +32,8 @@ def test_every_entry_point_cites_the_reference():
     for proc in ("lss_solve, src/nonlin_least_squares.f90:118-391", "ns_solve, src/nonlin_solve.f90:452-638",
                  "qns_solve, src/nonlin_solve.f90:156-425", "vfh_jac_fcn, src/nonlin_multi_eqn_mult_var.f90:198-277",
                  "vfh_fcn, src/nonlin_multi_eqn_mult_var.f90:178-195", "src/nonlin_types.f90:8-29",
-                 "cls_solve, src/nonlin_least_squares.f90:938-1176"):
+                 "cls_solve, src/nonlin_least_squares.f90:938-1176", "poly_fit, src/nonlin_polynomials.f90:146-199",
+                 "poly_eval_double, src/nonlin_polynomials.f90:256-283"):
         assert proc in HEADER
 
 

@@ -52,6 +52,23 @@ def test_constrained_least_squares_solver_settings():
     assert opt._obj.trust_region_radius == 2.5 and opt._obj.step_scaling_factor == 0.5
 
 
+def test_polynomial_object():
+    p = nb.polynomial()
+    assert p.order() == -1                                       # get_poly_order: unallocated -> -1 (:131-139)
+    p.initialize(3, B=5)
+    assert p.order() == 3 and p.get_all().shape == (4, 5) and np.all(p.get_all() == 0.0)
+    p.set(2, 1.5)
+    assert np.all(p.get(2) == 1.5) and np.all(p.get(1) == 0.0)  # 1-based, get(1) = c0
+    q = nb.polynomial([6.0, 1.0, -4.0, 1.0])                     # polynomial(c) constructor, tests/nonlin_test_poly.f90:61
+    assert q.order() == 3 and q.get_all().shape == (4, 1) and q.get(4)[0] == 1.0
+    with pytest.raises(nb.NonlinError):
+        nb.polynomial(-2)
+    with pytest.raises(nb.NonlinError):                          # y must be (npts, B)
+        p.fit(np.zeros(4), np.zeros(4), 2)
+    with pytest.raises(nb.NonlinError):                          # size(x) /= size(y): error stop 3
+        p.fit(np.zeros(5), np.zeros((4, 2)), 2)
+
+
 def test_quasi_newton_and_line_search_settings():
     s = nb.quasi_newton_solver()
     assert s.get_jacobian_interval() == 5                        # src/nonlin_solve.f90:51

@@ -178,6 +178,45 @@ def flops_per_system(w, sample=4096):
     return o.flops_total() / float(idx.size)
 
 
+def polyfit_extra(nb, torch, B, npts=21, order=3, steps=5):
+    """Batched polynomial%fit (README Example 3 shape: 21 shared abscissae, cubic) on device-resident data: a ring of
+    y buffers larger than L2, CUDA events around `steps` fits; CPU port on a slice for comparison."""
+    from nonlin_b200 import workloads as W
+    from oracle.nl_oracle import Oracle
+
+    w = W.WORKLOADS["C1"](B, seed=1000)
+    x = torch.from_numpy(W.POLYFIT_XP).cuda()
+    nring = max(2, int(np.ceil(768 * 2 ** 20 / (npts * B * 8))))
+    ys = [torch.from_numpy(w["args"]).cuda() for _ in range(nring)]
+    p = nb.polynomial()
+    st = torch.zeros(B, dtype=torch.int32, device="cuda")
+    for k in range(3):
+        p.fit(x, ys[k % nring], order, status=st)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for k in range(steps):
+        p.fit(x, ys[(3 + k) % nring], order, status=st)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    ok = int((st == 0).sum().item())
+    nsub = min(B, 1 << 18)
+    o = Oracle()
+    ysub = np.ascontiguousarray(w["args"][:, :nsub])
+    o.polyfit_batch(W.POLYFIT_XP, ysub[:, :4096].copy(), order)
+    t0 = time.perf_counter()
+    co, _ = o.polyfit_batch(W.POLYFIT_XP, ysub, order)
+    dt = time.perf_counter() - t0
+    same = bool(np.array_equal(p.get_all()[:, :nsub].cpu().numpy(), co))   # every ring slot holds the same data
+    bytes_alg = 8 * (npts + order + 1) + 4
+    return {"workload": "1M x polynomial%%fit, %d shared abscissae, order %d [SURVEY 8(f) widening POLY1], B=%d per GPU" % (npts, order, B),
+            "value": ok / (ms * 1e-3), "unit": "fits/s", "ms_per_step": ms, "kernel": "polyfit_kernel<4, smem>",
+            "hbm_gbps_algorithmic": B * bytes_alg / (ms * 1e-3) / 1e9, "bytes_per_fit": bytes_alg,
+            "cpu_port": {"value": nsub / dt, "unit": "fits/s", "cores": os.cpu_count() or 1, "sample": "%d fits" % nsub},
+            "bitwise_equal_to_cpu_port": same}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path.  The Fortran sources need gfortran + the external
     linalg package, neither of which exists in this image, so this arm times the C++ port (oracle/)."""
@@ -493,6 +532,11 @@ def run_engine(args):
                 del r
             except Exception as ex:   # an extra must never hide the headline
                 extras[name] = {"error": repr(ex)}
+
+        try:
+            extras["POLY1"] = polyfit_extra(nb, torch, BATCH_PER_GPU)
+        except Exception as ex:
+            extras["POLY1"] = {"error": repr(ex)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -16,7 +16,7 @@ module nonlin_batch
     private
     public :: nlb_engine, batch_vecfcn_helper, batch_iteration_behavior
     public :: batch_least_squares_solver, batch_newton_solver, batch_quasi_newton_solver, batch_line_search
-    public :: batch_constrained_least_squares_solver
+    public :: batch_constrained_least_squares_solver, batch_polynomial
     public :: NLB_OK, NL_NO_ERROR, NL_CONVERGENCE_ERROR, NL_DIVERGENT_BEHAVIOR_ERROR, &
         NL_SPURIOUS_CONVERGENCE_ERROR
 
@@ -83,6 +83,22 @@ module nonlin_batch
             integer(c_int), value :: fcn_id, m, n
             integer(c_int64_t), value :: b
             type(c_ptr), value :: x, fvec, sys, shared, ib, status, stream
+        end function
+        integer(c_int) function nlb_polynomial_fit_batch(handle, b, npts, order, thru_zero, x_is_shared, x, y, &
+                coeffs, status, stream) bind(C, name = "nlb_polynomial_fit_batch")
+            import :: c_ptr, c_int, c_int64_t
+            type(c_ptr), value :: handle
+            integer(c_int64_t), value :: b
+            integer(c_int), value :: npts, order, thru_zero, x_is_shared
+            type(c_ptr), value :: x, y, coeffs, status, stream
+        end function
+        integer(c_int) function nlb_polynomial_evaluate_batch(handle, b, order, npts, x_is_shared, coeffs, x, y, &
+                stream) bind(C, name = "nlb_polynomial_evaluate_batch")
+            import :: c_ptr, c_int, c_int64_t
+            type(c_ptr), value :: handle
+            integer(c_int64_t), value :: b
+            integer(c_int), value :: order, npts, x_is_shared
+            type(c_ptr), value :: coeffs, x, y, stream
         end function
         integer(c_int) function nlb_newton_solve_batch(handle, params, fcn_id, b, m, n, x, fvec, sys, &
                 shared, ib, status, stream) bind(C, name = "nlb_newton_solve_batch")
@@ -186,6 +202,16 @@ module nonlin_batch
         procedure, public :: set_trust_region_radius => bcls_set_radius
         procedure, public :: set_step_scaling_factor => bcls_set_factor
         procedure, public :: solve_batch => cls_solve_batch
+    end type
+
+    !> polynomial (nonlin_polynomials.f90:20-71) for B data sets: coefficients c(B, order + 1), c(:,1) = c0
+    type :: batch_polynomial
+        real(real64), allocatable, dimension(:,:) :: m_coeffs
+    contains
+        procedure, public :: order => bp_order
+        procedure, public :: fit => bp_fit
+        procedure, public :: fit_thru_zero => bp_fit_thru_zero
+        procedure, public :: evaluate => bp_evaluate
     end type
 
     type, abstract, extends(batch_equation_solver) :: batch_line_search_solver
@@ -438,6 +464,54 @@ contains
         ierr = nlb_constrained_least_squares_solve_batch(eng%handle, p, o, fcn%m_fcn, int(size(x, 1), c_int64_t), &
             int(fcn%m_nfcn, c_int), int(fcn%m_nvar, c_int), c_loc(x), c_loc(fvec), pa, ps, c_loc(ib), &
             c_loc(status), c_null_ptr)
+    end subroutine
+
+    pure function bp_order(this) result(n)
+        class(batch_polynomial), intent(in) :: this
+        integer(int32) :: n
+        n = -1
+        if (allocated(this%m_coeffs)) n = size(this%m_coeffs, 2) - 1
+    end function
+
+    !> `call p%fit(x, y, order)` for B data sets: x(npts) shared abscissae, y(B, npts); status(B) = 0 or 107.
+    subroutine bp_fit(this, eng, x, y, order, status, ierr)
+        class(batch_polynomial), intent(inout), target :: this
+        type(nlb_engine), intent(in) :: eng
+        real(real64), intent(in), dimension(:), contiguous, target :: x
+        real(real64), intent(in), dimension(:,:), contiguous, target :: y
+        integer(int32), intent(in) :: order
+        integer(int32), intent(out), dimension(:), target :: status
+        integer, intent(out) :: ierr
+        if (allocated(this%m_coeffs)) deallocate(this%m_coeffs)
+        allocate(this%m_coeffs(size(y, 1), order + 1))
+        ierr = nlb_polynomial_fit_batch(eng%handle, int(size(y, 1), c_int64_t), int(size(x), c_int), &
+            int(order, c_int), 0_c_int, 1_c_int, c_loc(x), c_loc(y), c_loc(this%m_coeffs), c_loc(status), c_null_ptr)
+    end subroutine
+
+    subroutine bp_fit_thru_zero(this, eng, x, y, order, status, ierr)
+        class(batch_polynomial), intent(inout), target :: this
+        type(nlb_engine), intent(in) :: eng
+        real(real64), intent(in), dimension(:), contiguous, target :: x
+        real(real64), intent(in), dimension(:,:), contiguous, target :: y
+        integer(int32), intent(in) :: order
+        integer(int32), intent(out), dimension(:), target :: status
+        integer, intent(out) :: ierr
+        if (allocated(this%m_coeffs)) deallocate(this%m_coeffs)
+        allocate(this%m_coeffs(size(y, 1), order + 1))
+        ierr = nlb_polynomial_fit_batch(eng%handle, int(size(y, 1), c_int64_t), int(size(x), c_int), &
+            int(order, c_int), 1_c_int, 1_c_int, c_loc(x), c_loc(y), c_loc(this%m_coeffs), c_loc(status), c_null_ptr)
+    end subroutine
+
+    !> `p%evaluate(x)`: yout(B, npts)
+    subroutine bp_evaluate(this, eng, x, yout, ierr)
+        class(batch_polynomial), intent(in), target :: this
+        type(nlb_engine), intent(in) :: eng
+        real(real64), intent(in), dimension(:), contiguous, target :: x
+        real(real64), intent(out), dimension(:,:), contiguous, target :: yout
+        integer, intent(out) :: ierr
+        ierr = nlb_polynomial_evaluate_batch(eng%handle, int(size(this%m_coeffs, 1), c_int64_t), &
+            int(this%order(), c_int), int(size(x), c_int), 1_c_int, c_loc(this%m_coeffs), c_loc(x), c_loc(yout), &
+            c_null_ptr)
     end subroutine
 
     subroutine ns_solve_batch(this, eng, fcn, x, fvec, ib, status, ierr, args, shared)

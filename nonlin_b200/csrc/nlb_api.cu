@@ -710,38 +710,67 @@ int nlb_polynomial_fit_batch(nlb_handle* h, int64_t B, int npts, int order, int 
     if ((rc = stage_in(h, 1, y, sizeof(double) * (size_t)npts * B, true, s, &ay))) return rc;
     if ((rc = stage_in(h, 2, coeffs, sizeof(double) * (size_t)(order + 1) * B, false, s, &ac))) return rc;
     if ((rc = stage_in(h, 5, status, sizeof(int32_t) * (size_t)B, false, s, &ast))) return rc;
-    // persistent grid: enough threads to fill the GPU, few enough that the live workspace stays near L2
-    static int threads_per_sm = 0;
-    if (threads_per_sm == 0) {
-        const char* e = std::getenv("NLB_POLYFIT_THREADS_PER_SM");   // tuning knob, multiple of 128
-        threads_per_sm = e ? std::atoi(e) : 1024;
-        if (threads_per_sm < 128) threads_per_sm = 128;
-    }
     const size_t per_thread = sizeof(double) * (size_t)npts * (size_t)(nc + 1);
-    long long T = (long long)h->num_sms * threads_per_sm;
-    const long long need = ((B + 127) / 128) * 128;
-    if (T > need) T = need;
-    const size_t budget = (size_t)2 << 30;
-    while (T > 128 && (size_t)T * per_thread > budget) T -= 128;
-    if ((size_t)T * per_thread > budget) return set_err(h, NLB_ERR_UNSUPPORTED, "polynomial fit: npts too large");
-    if (h->dwork_cap < (size_t)T * per_thread) {
-        NLB_CUDA(h, cudaStreamSynchronize(s));
-        if (h->dwork) NLB_CUDA(h, cudaFree(h->dwork));
-        h->dwork = nullptr;
-        h->dwork_cap = 0;
-        NLB_CUDA(h, cudaMalloc(&h->dwork, (size_t)T * per_thread));
-        h->dwork_cap = (size_t)T * per_thread;
-    }
-    const unsigned grid = (unsigned)(T / 128);
-    switch (nc) {
-#define X(NC)                                                                                                  \
-    case NC:                                                                                                   \
-        polyfit_kernel<NC><<<grid, 128, 0, s>>>(B, npts, thru_zero != 0, x_is_shared != 0, (const double*)ax.dev, \
-                                                (const double*)ay.dev, (double*)ac.dev, (int32_t*)ast.dev,      \
-                                                (double*)h->dwork);                                            \
+    const size_t smem_bytes = per_thread * 128;
+    const size_t smem_max = 225 * 1024;                      // of the 227 KB a CTA may opt in to
+    static int force_global = -1;
+    if (force_global < 0) force_global = std::getenv("NLB_POLYFIT_GLOBAL") ? 1 : 0;   // tuning knob
+    if (smem_bytes <= smem_max && !force_global) {
+        // shared-memory workspace: persistent grid of the CTAs that fit (each SM has 228 KB)
+        const int ctas_per_sm = (int)((228 * 1024) / (smem_bytes + 1024)) > 0 ? (int)((228 * 1024) / (smem_bytes + 1024)) : 1;
+        long long grid = (B + 127) / 128;
+        const long long resident = (long long)h->num_sms * ctas_per_sm;
+        if (grid > resident) grid = resident;
+        switch (nc) {
+#define X(NC)                                                                                                       \
+    case NC:                                                                                                        \
+        NLB_CUDA(h, cudaFuncSetAttribute(polyfit_kernel<NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                         (int)smem_bytes));                                                        \
+        polyfit_kernel<NC, true><<<(unsigned)grid, 128, smem_bytes, s>>>(                                           \
+            B, npts, thru_zero != 0, x_is_shared != 0, (const double*)ax.dev, (const double*)ay.dev,                \
+            (double*)ac.dev, (int32_t*)ast.dev, nullptr);                                                           \
         break;
-        X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
+            X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
 #undef X
+        }
+    } else {
+        // global workspace, persistent grid at full occupancy
+        static int threads_per_sm = -1;
+        if (threads_per_sm < 0) {
+            const char* e = std::getenv("NLB_POLYFIT_THREADS_PER_SM");   // tuning knob, multiple of 128
+            threads_per_sm = e ? std::atoi(e) : 0;
+        }
+        long long T;
+        if (threads_per_sm > 0) {
+            T = (long long)h->num_sms * threads_per_sm;
+        } else {
+            // measured (B200, 100 x 6 and 512 x 6 fits): full occupancy beats keeping the workspace inside L2
+            T = (long long)h->num_sms * 2048;
+        }
+        const long long need = ((B + 127) / 128) * 128;
+        if (T > need) T = need;
+        const size_t budget = (size_t)2 << 30;
+        while (T > 128 && (size_t)T * per_thread > budget) T -= 128;
+        if ((size_t)T * per_thread > budget) return set_err(h, NLB_ERR_UNSUPPORTED, "polynomial fit: npts too large");
+        if (h->dwork_cap < (size_t)T * per_thread) {
+            NLB_CUDA(h, cudaStreamSynchronize(s));
+            if (h->dwork) NLB_CUDA(h, cudaFree(h->dwork));
+            h->dwork = nullptr;
+            h->dwork_cap = 0;
+            NLB_CUDA(h, cudaMalloc(&h->dwork, (size_t)T * per_thread));
+            h->dwork_cap = (size_t)T * per_thread;
+        }
+        const unsigned grid = (unsigned)(T / 128);
+        switch (nc) {
+#define X(NC)                                                                                                       \
+    case NC:                                                                                                        \
+        polyfit_kernel<NC, false><<<grid, 128, 0, s>>>(B, npts, thru_zero != 0, x_is_shared != 0,                   \
+                                                       (const double*)ax.dev, (const double*)ay.dev,                \
+                                                       (double*)ac.dev, (int32_t*)ast.dev, (double*)h->dwork);      \
+        break;
+            X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
+#undef X
+        }
     }
     ++h->launches;
     NLB_CUDA(h, cudaGetLastError());

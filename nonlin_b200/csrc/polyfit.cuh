@@ -10,9 +10,10 @@
 // as DORM2R('L','T') does, DTRTRS's exact-zero diagonal test, DTRSM, and the scaling undone.
 //
 // Mapping.  The m x n Vandermonde matrix and the right-hand side (n + 1 columns of m rows) of one data set live in
-// a global-memory workspace laid out [column][row][thread]: lane-contiguous, so every pass of the factorisation is
-// a fully coalesced stream, and the grid is capped (persistent, grid-stride over data sets) so that the live
-// workspace stays near the 126 MB L2.  H(i) is applied to y in the same two passes that apply it to the trailing
+// a workspace laid out [column][row][thread]: lane-contiguous, so every pass of the factorisation is conflict-free
+// in shared memory and fully coalesced in global memory.  Small fits (128 threads' workspaces fit one CTA's shared
+// memory: m (n + 1) <= 220 doubles) run out of shared memory; larger ones use a global workspace with the grid
+// capped (persistent, grid-stride over data sets) so that the live workspace stays inside the 126 MB L2.  H(i) is applied to y in the same two passes that apply it to the trailing
 // columns of A (LAPACK does it afterwards; v_i is final by then either way, so the arithmetic is identical), each
 // column's dot product accumulating in row order.  Algorithmic HBM bytes per data set: 8 (m + m + n) (+ 4 status)
 // with per-set abscissae, 8 (m + n) with shared ones.
@@ -22,6 +23,16 @@
 namespace nlb {
 
 constexpr int POLY_MAX_COLS = 8;
+// rows fetched per batch in the factorisation passes, and the register cap of the global-workspace variant
+#ifndef NLB_POLY_RB_SMEM
+#define NLB_POLY_RB_SMEM 4
+#endif
+#ifndef NLB_POLY_RB_GLOBAL
+#define NLB_POLY_RB_GLOBAL 2
+#endif
+#ifndef NLB_POLY_GLOBAL_MINB
+#define NLB_POLY_GLOBAL_MINB 4
+#endif
 constexpr int LA_INVALID_OPERATION_ERROR = 107;   // linalg's code for a rank-deficient solve_least_squares
 
 // DLASCL('G') multiplier sequence: calls apply(mul) one or more times so that the product of the multipliers is
@@ -63,19 +74,24 @@ NLB_DEV void dlascl_apply(double cfrom, double cto, Fn apply) {
     }
 }
 
-template <int NC>
-__global__ void __launch_bounds__(128)
+template <int NC, bool SMEM>
+__global__ void __launch_bounds__(128, SMEM ? 1 : NLB_POLY_GLOBAL_MINB)
 polyfit_kernel(long long B, int npts, int thru_zero, int x_shared, const double* __restrict__ x,
                const double* __restrict__ y, double* __restrict__ coeffs, int32_t* __restrict__ status,
                double* __restrict__ work) {
-    const long long T = (long long)gridDim.x * blockDim.x;
+    // Workspace of this thread: column c, row r at W[(c * npts + r) * T].  SMEM: the CTA's dynamic shared memory
+    // (T = 128 lanes, conflict-free); otherwise the global workspace (T = all threads of the grid, coalesced).
+    extern __shared__ double pf_smem[];
+    constexpr int RB = SMEM ? NLB_POLY_RB_SMEM : NLB_POLY_RB_GLOBAL;
+    const long long GT = (long long)gridDim.x * blockDim.x;
     const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    double* const W = work + tid;
+    const long long T = SMEM ? (long long)blockDim.x : GT;
+    double* const W = SMEM ? pf_smem + threadIdx.x : work + tid;
     const long long cs = (long long)npts * T;         // column stride; row stride is T
 #define PF_AT(r, c) W[(long long)(c) * cs + (long long)(r) * T]
     const double smlnum = 0x1p-970, bignum = 0x1p970;  // dlamch('S') / dlamch('P') and its reciprocal
 
-    for (long long b = tid; b < B; b += T) {
+    for (long long b = tid; b < B; b += GT) {
         // Vandermonde columns and the right-hand side; DLANGE('M') of both on the way
         double anrm = 0.0, bnrm = 0.0;
         for (int r = 0; r < npts; ++r) {
@@ -132,7 +148,17 @@ polyfit_kernel(long long B, int npts, int thru_zero, int x_shared, const double*
                 double tau = 0.0;
                 if (npts - i > 1) {
                     Dnrm2 acc;
-                    for (int r = i + 1; r < npts; ++r) acc.add(PF_AT(r, i));
+                    {
+                        int r = i + 1;
+                        for (; r + RB <= npts; r += RB) {
+                            double t[RB];
+#pragma unroll
+                            for (int k = 0; k < RB; ++k) t[k] = PF_AT(r + k, i);
+#pragma unroll
+                            for (int k = 0; k < RB; ++k) acc.add(t[k]);
+                        }
+                        for (; r < npts; ++r) acc.add(PF_AT(r, i));
+                    }
                     double xnorm = acc.value();
                     if (xnorm != 0.0) {
                         double alpha = PF_AT(i, i);
@@ -154,7 +180,17 @@ polyfit_kernel(long long B, int npts, int thru_zero, int x_shared, const double*
                         }
                         tau = (beta - alpha) / beta;
                         const double sc = 1.0 / (alpha - beta);
-                        for (int r = i + 1; r < npts; ++r) PF_AT(r, i) = sc * PF_AT(r, i);
+                        {
+                            int r = i + 1;
+                            for (; r + RB <= npts; r += RB) {
+                                double t[RB];
+#pragma unroll
+                                for (int k = 0; k < RB; ++k) t[k] = PF_AT(r + k, i);
+#pragma unroll
+                                for (int k = 0; k < RB; ++k) PF_AT(r + k, i) = sc * t[k];
+                            }
+                            for (; r < npts; ++r) PF_AT(r, i) = sc * PF_AT(r, i);
+                        }
                         for (int j = 0; j < knt; ++j) beta = beta * safmin;
                         PF_AT(i, i) = beta;
                     }
@@ -170,29 +206,72 @@ polyfit_kernel(long long B, int npts, int thru_zero, int x_shared, const double*
                         if (PF_AT(r, c) != 0.0) { lastc = c - i; break; }
                 bool ylive = false;
                 for (int r = i; r < i + lastv && !ylive; ++r) ylive = PF_AT(r, NC) != 0.0;
-                // w = C^T v for every live column (DGEMV 'T'), each sum in row order
+                // w = C^T v for every live column (DGEMV 'T'), each sum in row order.  Rows are fetched RB at a
+                // time (all loads of a batch in flight together) and then consumed in order.
+                const int rend = i + lastv;
+                bool live[NC + 1];
+#pragma unroll
+                for (int c = 0; c <= NC; ++c) live[c] = (c == NC) ? ylive : (c > i && c - i <= lastc);
                 double w[NC + 1];
 #pragma unroll
                 for (int c = 0; c <= NC; ++c) w[c] = 0.0;
-                for (int r = i; r < i + lastv; ++r) {
-                    const double v = (r == i) ? 1.0 : PF_AT(r, i);
 #pragma unroll
-                    for (int c = 1; c < NC; ++c)
-                        if (c > i && c - i <= lastc) w[c] += PF_AT(r, c) * v;
-                    if (ylive) w[NC] += PF_AT(r, NC) * v;
+                for (int c = 1; c <= NC; ++c)
+                    if (live[c]) w[c] += PF_AT(i, c) * 1.0;            // row i: v(i) = 1
+                int r = i + 1;
+                for (; r + RB <= rend; r += RB) {
+                    double vv[RB], aa[RB][NC + 1];
+#pragma unroll
+                    for (int k = 0; k < RB; ++k) {
+                        vv[k] = PF_AT(r + k, i);
+#pragma unroll
+                        for (int c = 1; c <= NC; ++c)
+                            if (c > i) aa[k][c] = PF_AT(r + k, c);
+                    }
+#pragma unroll
+                    for (int k = 0; k < RB; ++k) {
+#pragma unroll
+                        for (int c = 1; c <= NC; ++c)
+                            if (live[c]) w[c] += aa[k][c] * vv[k];
+                    }
+                }
+                for (; r < rend; ++r) {
+                    const double v = PF_AT(r, i);
+#pragma unroll
+                    for (int c = 1; c <= NC; ++c)
+                        if (live[c]) w[c] += PF_AT(r, c) * v;
                 }
                 // C := C - tau v w^T (DGER, zero entries of w skipped)
                 bool any = false;
 #pragma unroll
                 for (int c = 1; c <= NC; ++c) {
-                    const bool live = (c == NC) ? ylive : (c > i && c - i <= lastc);
                     const double wc = 0.0 + 1.0 * w[c];
-                    w[c] = (live && wc != 0.0) ? (-tau) * wc : 0.0;
+                    w[c] = (live[c] && wc != 0.0) ? (-tau) * wc : 0.0;
                     any = any || w[c] != 0.0;
                 }
                 if (!any) continue;
-                for (int r = i; r < i + lastv; ++r) {
-                    const double v = (r == i) ? 1.0 : PF_AT(r, i);
+#pragma unroll
+                for (int c = 1; c <= NC; ++c)
+                    if (w[c] != 0.0) PF_AT(i, c) = PF_AT(i, c) + 1.0 * w[c];
+                r = i + 1;
+                for (; r + RB <= rend; r += RB) {
+                    double vv[RB], aa[RB][NC + 1];
+#pragma unroll
+                    for (int k = 0; k < RB; ++k) {
+                        vv[k] = PF_AT(r + k, i);
+#pragma unroll
+                        for (int c = 1; c <= NC; ++c)
+                            if (c > i) aa[k][c] = PF_AT(r + k, c);
+                    }
+#pragma unroll
+                    for (int k = 0; k < RB; ++k) {
+#pragma unroll
+                        for (int c = 1; c <= NC; ++c)
+                            if (w[c] != 0.0) PF_AT(r + k, c) = aa[k][c] + vv[k] * w[c];
+                    }
+                }
+                for (; r < rend; ++r) {
+                    const double v = PF_AT(r, i);
 #pragma unroll
                     for (int c = 1; c <= NC; ++c)
                         if (w[c] != 0.0) PF_AT(r, c) = PF_AT(r, c) + v * w[c];

@@ -201,4 +201,38 @@ protected:
     }
 };
 
+// reference src/nonlin_polynomials.f90:20-71 — a batch of B polynomials of one order; coefficients
+// c[k*B + b], k = 0..order (get(i) of the reference is row i - 1).  Host buffers.
+class polynomial {
+public:
+    int order() const { return order_; }
+    int64_t count() const { return B_; }
+    const std::vector<double>& get_all() const { return c_; }
+    double get(int i, int64_t b = 0) const { return c_[(size_t)(i - 1) * B_ + b]; }
+    void set(int i, double v, int64_t b = 0) { c_[(size_t)(i - 1) * B_ + b] = v; }
+    void initialize(int order, int64_t B = 1) {
+        if (order < 0) throw error(NLB_ERR_INVALID_ARGUMENT, "order must be >= 0");
+        order_ = order; B_ = B; c_.assign((size_t)(order + 1) * B, 0.0);
+    }
+    // `call p%fit(x, y, order)` / `p%fit_thru_zero`: y[i*B + b]; x[i] (shared) or x[i*B + b]; host or device pointers
+    void fit(const engine& eng, int64_t B, int npts, const double* x, bool x_is_shared, const double* y, int order,
+             int32_t* status = nullptr, bool thru_zero = false) {
+        initialize(order, B);
+        eng.check(nlb_polynomial_fit_batch(eng.get(), B, npts, order, thru_zero, x_is_shared, x, y, c_.data(), status,
+                                           nullptr));
+    }
+    void fit_thru_zero(const engine& eng, int64_t B, int npts, const double* x, bool x_is_shared, const double* y,
+                       int order, int32_t* status = nullptr) {
+        fit(eng, B, npts, x, x_is_shared, y, order, status, true);
+    }
+    // `p%evaluate(x)`: yout[i*B + b]
+    void evaluate(const engine& eng, int npts, const double* x, bool x_is_shared, double* yout) const {
+        eng.check(nlb_polynomial_evaluate_batch(eng.get(), B_, order_, npts, x_is_shared, c_.data(), x, yout, nullptr));
+    }
+private:
+    int order_ = -1;
+    int64_t B_ = 0;
+    std::vector<double> c_;
+};
+
 }  // namespace nonlin

@@ -43,6 +43,26 @@ int main() {
                 return 1;
             }
         }
+        // README Example 3: cubic through the 21 points of Example 2, c0 = 1.1866141861 ... c3 = 1.0647628218
+        const double xp[21] = {0.0, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0,
+                               1.1, 1.2, 1.3, 1.4, 1.5, 1.6, 1.7, 1.8, 1.9, 2.0};
+        const double yp[21] = {1.216737514, 1.250032542, 1.305579195, 1.040182335, 1.751867738, 1.109716707,
+                               2.018141531, 1.992418729, 1.807916923, 2.078806005, 2.698801324, 2.644662712,
+                               3.412756702, 4.406137221, 4.567156645, 4.999550779, 5.652854194, 6.784320119,
+                               8.307936836, 8.395126494, 10.30252404};
+        std::vector<double> yb(21 * B);
+        for (int i = 0; i < 21; ++i)
+            for (int64_t b = 0; b < B; ++b) yb[i * B + b] = yp[i];
+        nonlin::polynomial poly;
+        poly.fit(eng, B, 21, xp, true, yb.data(), 3, statusc.data());
+        const double want[4] = {1.1866141861, 0.4466136311, -0.1223204989, 1.0647628218};
+        for (int k = 0; k < 4; ++k) {
+            const double d = poly.get(k + 1, B - 1) - want[k];
+            if (statusc[B - 1] != 0 || d > 5e-11 || d < -5e-11) {
+                std::printf("FAIL (polynomial fit) c%d = %.12f\n", k, poly.get(k + 1, B - 1));
+                return 1;
+            }
+        }
         std::printf("Solution: (%.5f, %.5f)\nResidual: (%.3e, %.3e)\nIterations: %d\nFunction Evaluations: %d\nJacobian Evaluations: %d\n",
                     x[0], x[B], f[0], f[B], ib[0].iter_count, ib[0].fcn_count, ib[0].jacobian_count);
     } catch (const nonlin::error& e) {

@@ -9,7 +9,8 @@ kw = {"m": int(os.environ.get("NLB_M", "4096"))} if name == "C4" else {}
 w = W.WORKLOADS[name](B, **kw)
 obj = nb.vecfcn_helper(); obj.set_fcn(w["fcn"], w["m"], w["n"])
 if w["shared"] is not None: obj.set_shared_data(torch.from_numpy(w["shared"]).cuda())
-s = {"least_squares": nb.least_squares_solver, "newton": nb.newton_solver, "quasi_newton": nb.quasi_newton_solver}[w["solver"]]()
+s = {"least_squares": nb.least_squares_solver, "newton": nb.newton_solver, "quasi_newton": nb.quasi_newton_solver,
+     "constrained_least_squares": nb.constrained_least_squares_solver}[w["solver"]]()
 for k, v in w["settings"].items(): getattr(s, k)(v)
 x0 = torch.from_numpy(w["x0"]).cuda(); args = None if w["args"] is None else torch.from_numpy(w["args"]).cuda()
 f = torch.empty((w["m"], B), dtype=torch.float64, device="cuda"); ib = nb.iteration_behavior(B, like=x0); st = torch.zeros(B, dtype=torch.int32, device="cuda")

@@ -188,6 +188,40 @@ int nlb_polynomial_fit_batch(nlb_handle* handle, int64_t B, int npts, int order,
 int nlb_polynomial_evaluate_batch(nlb_handle* handle, int64_t B, int order, int npts, int x_is_shared,
                                   const double* coeffs, const double* x, double* y, void* stream);
 
+/* One-variable solvers.  Settings = the members of equation_solver_1var
+ * (src/nonlin_single_var.f90:44-54: set_max_fcn_evals :227, set_fcn_tolerance :248, set_var_tolerance :268,
+ * set_diff_tolerance :311) plus "fcn1var_helper%set_diff was called" (:203-211). */
+typedef struct nlb_params_1var {
+    int32_t max_fcn_evals;      /* 100   */
+    double fcn_tol;             /* 1e-8  */
+    double var_tol;             /* 1e-12 */
+    double diff_tol;            /* 1e-12 */
+    int32_t use_analytic_diff;  /* 0: forward difference of f1h_diff_fcn (:154-200) */
+} nlb_params_1var;
+void nlb_params_1var_default(nlb_params_1var* p);
+
+/* Registry of compiled-in one-variable functions: the analogue of fcn1var_helper%set_fcn (:132-140). */
+int nlb_fcn1var_count(void);
+int nlb_fcn1var_lookup(const char* name);            /* id or -1 */
+const char* nlb_fcn1var_name(int fcn_id);            /* NULL if unknown */
+int nlb_fcn1var_info(int fcn_id, int* args_len, int* has_derivative);
+
+/* brent_solver%solve  (brent_solve, src/nonlin_solve.f90:643-835) and newton_1var_solver%solve  (newt1var_solve,
+ * src/nonlin_solve.f90:840-1032) over B independent equations f(x; args_b) = 0.
+ *   lim1, lim2   the value_pair of each equation (search limits, either order), B doubles each
+ *   x            in/out, B doubles: the root.  Brent ignores the input and returns 0 where it fails, as the
+ *                reference does; Newton leaves x untouched where the limits are rejected
+ *   f            out, B doubles, or NULL = the reference's optional `f` absent (Newton then counts one evaluation less)
+ *   args         per-equation data args[k*B + b] (`class(*) args`), NULL if the function takes none
+ *   status       0, NLB_INVALID_INPUT_ERROR (|lim1 - lim2| < epsilon, :713 / :899) or NLB_CONVERGENCE_ERROR (:813, :1004)
+ * ib%jacobian_count carries Newton's derivative-evaluation count, as in the reference (:1022). */
+int nlb_brent_solve_batch(nlb_handle* handle, const nlb_params_1var* params, int fcn_id, int64_t B, const double* lim1,
+                          const double* lim2, double* x, double* f, const double* args, nlb_iteration_behavior* ib,
+                          int32_t* status, void* stream);
+int nlb_newton_1var_solve_batch(nlb_handle* handle, const nlb_params_1var* params, int fcn_id, int64_t B,
+                                const double* lim1, const double* lim2, double* x, double* f, const double* args,
+                                nlb_iteration_behavior* ib, int32_t* status, void* stream);
+
 /* vecfcn_helper%fcn  (vfh_fcn, src/nonlin_multi_eqn_mult_var.f90:178-195) over B points. */
 int nlb_vecfcn_eval_batch(nlb_handle* handle, int fcn_id, int64_t B, int m, int n, const double* x, double* fvec,
                           const double* sys, const double* shared, void* stream);

@@ -28,16 +28,22 @@ from .api import (  # noqa: F401
     NonlinError,
     constrained_equation_solver,
     constrained_least_squares_solver,
+    brent_solver,
     default_engine,
+    equation_solver_1var,
+    fcn1var_helper,
+    fcn1var_names,
     equation_solver,
     ib_view,
     iteration_behavior,
     least_squares_solver,
     line_search,
     line_search_solver,
+    newton_1var_solver,
     newton_solver,
     polynomial,
     quasi_newton_solver,
+    value_pair,
     vecfcn_helper,
     vecfcn_names,
 )

@@ -44,6 +44,8 @@ EXPORTS = [
     "nlb_vecfcn_eval_batch", "nlb_jacobian_batch", "nlb_reduce_stats", "nlb_measure_fp64_peak",
     "nlb_measure_fp64_latency", "nlb_constrained_options_default", "nlb_constrained_least_squares_solve_batch",
     "nlb_polynomial_fit_batch", "nlb_polynomial_evaluate_batch",
+    "nlb_params_1var_default", "nlb_fcn1var_count", "nlb_fcn1var_lookup", "nlb_fcn1var_name", "nlb_fcn1var_info",
+    "nlb_brent_solve_batch", "nlb_newton_1var_solve_batch",
 ]
 
 
@@ -61,6 +63,16 @@ class nlb_params(C.Structure):
         ("ls_factor", C.c_double),
         ("use_analytic_jacobian", C.c_int32),
         ("max_iter_guard", C.c_int32),
+    ]
+
+
+class nlb_params_1var(C.Structure):
+    _fields_ = [
+        ("max_fcn_evals", C.c_int32),
+        ("fcn_tol", C.c_double),
+        ("var_tol", C.c_double),
+        ("diff_tol", C.c_double),
+        ("use_analytic_diff", C.c_int32),
     ]
 
 
@@ -116,6 +128,14 @@ def load():
         [vp, C.POINTER(nlb_params), C.POINTER(nlb_constrained_options)] + solve_args[2:])
     lib.nlb_polynomial_fit_batch.argtypes = [vp, i64, i32, i32, i32, i32, vp, vp, vp, vp, vp]
     lib.nlb_polynomial_evaluate_batch.argtypes = [vp, i64, i32, i32, i32, vp, vp, vp, vp]
+    lib.nlb_params_1var_default.argtypes = [C.POINTER(nlb_params_1var)]
+    lib.nlb_params_1var_default.restype = None
+    lib.nlb_fcn1var_lookup.argtypes = [C.c_char_p]
+    lib.nlb_fcn1var_name.argtypes = [i32]
+    lib.nlb_fcn1var_name.restype = C.c_char_p
+    lib.nlb_fcn1var_info.argtypes = [i32, C.POINTER(i32), C.POINTER(i32)]
+    for name in ("nlb_brent_solve_batch", "nlb_newton_1var_solve_batch"):
+        getattr(lib, name).argtypes = [vp, C.POINTER(nlb_params_1var), i32, i64, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.nlb_vecfcn_eval_batch.argtypes = [vp, i32, i64, i32, i32, vp, vp, vp, vp, vp]
     lib.nlb_jacobian_batch.argtypes = [vp, C.POINTER(nlb_params), i32, i64, i32, i32, vp, vp, vp, vp, vp]
     lib.nlb_reduce_stats.argtypes = [vp, i64, vp, vp, vp, vp]

@@ -574,6 +574,146 @@ class newton_solver(line_search_solver):
     _entry = "nlb_newton_solve_batch"
 
 
+class value_pair:
+    """A pair of values per equation: the search limits of the one-variable solvers (reference `value_pair`,
+    src/nonlin_types.f90:31-37).  x1, x2: scalars (broadcast over the batch) or (B,) arrays."""
+
+    def __init__(self, x1=0.0, x2=0.0):
+        self.x1 = x1
+        self.x2 = x2
+
+
+class fcn1var_helper:
+    """Names a registered one-variable function (reference `fcn1var_helper`, src/nonlin_single_var.f90:25-41)."""
+
+    def __init__(self):
+        self._fcn_id = -1
+        self._info = None
+        self._use_diff = False
+
+    def set_fcn(self, fcn):
+        fid = _LIB.nlb_fcn1var_lookup(fcn.encode()) if isinstance(fcn, str) else int(fcn)
+        a, d = C.c_int(), C.c_int()
+        if fid < 0 or _LIB.nlb_fcn1var_info(fid, C.byref(a), C.byref(d)) != _lib.NLB_OK:
+            raise NonlinError(_lib.NLB_ERR_UNKNOWN_FCN, "one-variable function %r is not registered" % (fcn,))
+        self._fcn_id = fid
+        self._info = {"args_len": a.value, "has_diff": bool(d.value)}
+        self._use_diff = False
+
+    def set_diff(self, enable=True):
+        """`call obj%set_diff(diff)`: use the registered derivative instead of the forward difference (:203-211)."""
+        if enable and not (self._info and self._info["has_diff"]):
+            raise NonlinError(_lib.NLB_ERR_UNSUPPORTED, "no derivative is registered for this function")
+        self._use_diff = bool(enable)
+
+    def is_fcn_defined(self):
+        return self._fcn_id >= 0
+
+    def is_derivative_defined(self):
+        return self._use_diff
+
+
+def fcn1var_names():
+    return [_LIB.nlb_fcn1var_name(i).decode() for i in range(_LIB.nlb_fcn1var_count())]
+
+
+class equation_solver_1var:
+    """Base of the one-variable solvers (reference src/nonlin_single_var.f90:43-69)."""
+
+    _entry = None
+
+    def __init__(self, engine=None):
+        self._engine = engine
+        self._max_eval = 100
+        self._fcn_tol = 1.0e-8
+        self._xtol = 1.0e-12
+        self._difftol = 1.0e-12
+        self._print_status = False
+
+    def get_max_fcn_evals(self):
+        return self._max_eval
+
+    def set_max_fcn_evals(self, n):
+        self._max_eval = int(n)
+
+    def get_fcn_tolerance(self):
+        return self._fcn_tol
+
+    def set_fcn_tolerance(self, x):
+        self._fcn_tol = float(x)
+
+    def get_var_tolerance(self):
+        return self._xtol
+
+    def set_var_tolerance(self, x):
+        self._xtol = float(x)
+
+    def get_diff_tolerance(self):
+        return self._difftol
+
+    def set_diff_tolerance(self, x):
+        self._difftol = float(x)
+
+    def get_print_status(self):
+        return self._print_status
+
+    def set_print_status(self, x):
+        self._print_status = bool(x)      # stored, not acted on (device-resident iterations)
+
+    def solve(self, fcn, x, lim, f=None, ib=None, args=None, status=None, stream=None, want_f=True):
+        """`call solver%solve(fcn, x, lim, f, ib, args)` over the B equations of x (B,), in place.
+
+        lim: a `value_pair` whose members are scalars or (B,) arrays.  f: (B,) output; with `want_f=False` the
+        reference's optional `f` is treated as absent.  Returns the per-equation status array."""
+        if not fcn.is_fcn_defined():
+            raise NonlinError(_lib.NLB_ERR_UNKNOWN_FCN, "no function set (NL_UNDEFINED_FUNCTION_ERROR)")
+        if x.ndim != 1:
+            raise NonlinError(_lib.NLB_ERR_SIZE, "x must be (B,)")
+        B = x.shape[0]
+        _check_f64("x", x, (B,))
+
+        def limits(v, name):
+            if np.ndim(v) == 0:
+                a = _empty_like(x, (B,))
+                a[...] = float(v)
+                return a
+            _check_f64(name, v, (B,))
+            return v
+
+        l1, l2 = limits(lim.x1, "lim%x1"), limits(lim.x2, "lim%x2")
+        if f is None and want_f:
+            f = _empty_like(x, (B,))
+        if f is not None:
+            _check_f64("f", f, (B,))
+        if args is not None:
+            _check_f64("args", args, (fcn._info["args_len"], B))
+        if status is None:
+            status = _empty_like(x, (B,), dtype="int32")
+            status[...] = 0
+        eng = self._engine or default_engine(_device_of(x, f, args, ib, status) or 0)
+        p = _lib.nlb_params_1var()
+        _LIB.nlb_params_1var_default(C.byref(p))
+        p.max_fcn_evals, p.fcn_tol, p.var_tol, p.diff_tol = self._max_eval, self._fcn_tol, self._xtol, self._difftol
+        p.use_analytic_diff = int(fcn.is_derivative_defined())
+        entry = getattr(_LIB, self._entry)
+        eng.check(entry(eng._h, C.byref(p), fcn._fcn_id, B, _ptr(l1), _ptr(l2), _ptr(x), _ptr(f), _ptr(args), _ptr(ib),
+                        _ptr(status), C.c_void_p(stream) if stream is not None else _stream_of(x, f, args, ib, status)))
+        self.last_f = f
+        return status
+
+
+class brent_solver(equation_solver_1var):
+    """Brent's method (reference src/nonlin_solve.f90:69-76, brent_solve :643-835)."""
+
+    _entry = "nlb_brent_solve_batch"
+
+
+class newton_1var_solver(equation_solver_1var):
+    """Newton's method safeguarded by bisection (reference src/nonlin_solve.f90:78-85, newt1var_solve :840-1032)."""
+
+    _entry = "nlb_newton_1var_solve_batch"
+
+
 class polynomial:
     """A batch of B polynomials of one order, c0 + c1 x + ... (reference `polynomial`,
     src/nonlin_polynomials.f90:20-71): `fit`, `fit_thru_zero`, `evaluate`, `order`, `get`, `get_all`, `set`,

@@ -13,6 +13,7 @@
 
 #include "coop_kernels.cuh"
 #include "polyfit.cuh"
+#include "scalar_solvers.cuh"
 #include "tps_cls.cuh"
 #include "tps_lm.cuh"
 #include "tps_newton_broyden.cuh"
@@ -423,6 +424,65 @@ int dispatch_cls(nlb_handle* h, int fcn_id, const DevParams& p, const DevCls& o,
     return NLB_OK;
 }
 
+int ensure_device(nlb_handle* h);
+
+#define NLB_FCN1_LIST(X) X(SinxDivX) X(SinxDivXA) X(CubicWallis) X(ExpMinusX) X(CubicArgs)
+
+int solve_1var_batch(nlb_handle* h, int solver, const nlb_params_1var* params, int fcn_id, int64_t B,
+                     const double* lim1, const double* lim2, double* x, double* f, const double* args,
+                     nlb_iteration_behavior* ib, int32_t* status, void* stream) {
+    if (!h) return NLB_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(h->mu);
+    if (!params || B < 0 || (B > 0 && (!x || !lim1 || !lim2)))
+        return set_err(h, NLB_ERR_INVALID_ARGUMENT, "null argument or B < 0");
+    if (fcn_id < 0 || fcn_id >= FCN1_COUNT) return set_err(h, NLB_ERR_UNKNOWN_FCN, "unknown one-variable function id");
+    const Fcn1Info& fi = fcn1_table()[fcn_id];
+    if (fi.args_len > 0 && B > 0 && !args) return set_err(h, NLB_ERR_INVALID_ARGUMENT, "this function needs per-equation args");
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    if (B == 0) return NLB_OK;
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    Staged a1, a2, ax, af, aa, aib, ast;
+    if ((rc = stage_in(h, 0, x, sizeof(double) * (size_t)B, true, s, &ax))) return rc;
+    if ((rc = stage_in(h, 1, f, sizeof(double) * (size_t)B, false, s, &af))) return rc;
+    if ((rc = stage_in(h, 2, args, sizeof(double) * (size_t)fi.args_len * B, true, s, &aa))) return rc;
+    if ((rc = stage_in(h, 3, lim1, sizeof(double) * (size_t)B, true, s, &a1))) return rc;
+    if ((rc = stage_in(h, 6, lim2, sizeof(double) * (size_t)B, true, s, &a2))) return rc;
+    if ((rc = stage_in(h, 4, ib, sizeof(nlb_iteration_behavior) * (size_t)B, false, s, &aib))) return rc;
+    if ((rc = stage_in(h, 5, status, sizeof(int32_t) * (size_t)B, false, s, &ast))) return rc;
+    DevParams1 p;
+    p.max_fcn_evals = params->max_fcn_evals;
+    p.fcn_tol = params->fcn_tol;
+    p.var_tol = params->var_tol;
+    p.diff_tol = params->diff_tol;
+    p.use_analytic_diff = params->use_analytic_diff;
+    const unsigned grid = (unsigned)((B + 127) / 128);
+    switch (fcn_id) {
+#define X(F)                                                                                                      \
+    case F::ID:                                                                                                   \
+        if (solver == 0)                                                                                          \
+            solve_1var_kernel<F, 0><<<grid, 128, 0, s>>>(p, B, (const double*)a1.dev, (const double*)a2.dev,      \
+                                                         (double*)ax.dev, (double*)af.dev, (const double*)aa.dev, \
+                                                         (nlb_iteration_behavior*)aib.dev, (int32_t*)ast.dev);    \
+        else                                                                                                      \
+            solve_1var_kernel<F, 1><<<grid, 128, 0, s>>>(p, B, (const double*)a1.dev, (const double*)a2.dev,      \
+                                                         (double*)ax.dev, (double*)af.dev, (const double*)aa.dev, \
+                                                         (nlb_iteration_behavior*)aib.dev, (int32_t*)ast.dev);    \
+        break;
+        NLB_FCN1_LIST(X)
+#undef X
+    }
+    ++h->launches;
+    NLB_CUDA(h, cudaGetLastError());
+    if ((rc = stage_out(h, ax, s))) return rc;
+    if ((rc = stage_out(h, af, s))) return rc;
+    if ((rc = stage_out(h, aib, s))) return rc;
+    if ((rc = stage_out(h, ast, s))) return rc;
+    if (a1.staged || a2.staged || ax.staged || af.staged || aa.staged || aib.staged || ast.staged)
+        NLB_CUDA(h, cudaStreamSynchronize(s));
+    return NLB_OK;
+}
+
 int check_sizes(nlb_handle* h, int fcn_id, int* m, int* n, int* sys_len, int* shared_len) {
     if (fcn_id < 0 || fcn_id >= FCN_COUNT) return set_err(h, NLB_ERR_UNKNOWN_FCN, "unknown residual id");
     const FcnInfo& fi = fcn_table()[fcn_id];
@@ -804,6 +864,48 @@ int nlb_polynomial_evaluate_batch(nlb_handle* h, int64_t B, int order, int npts,
     if ((rc = stage_out(h, ay, s))) return rc;
     if (ax.staged || ay.staged || ac.staged) NLB_CUDA(h, cudaStreamSynchronize(s));
     return NLB_OK;
+}
+
+void nlb_params_1var_default(nlb_params_1var* p) {
+    if (!p) return;
+    p->max_fcn_evals = 100;
+    p->fcn_tol = 1.0e-8;
+    p->var_tol = 1.0e-12;
+    p->diff_tol = 1.0e-12;
+    p->use_analytic_diff = 0;
+}
+
+int nlb_fcn1var_count(void) { return FCN1_COUNT; }
+
+int nlb_fcn1var_lookup(const char* name) {
+    if (!name) return -1;
+    for (int i = 0; i < FCN1_COUNT; ++i)
+        if (std::strcmp(fcn1_table()[i].name, name) == 0) return i;
+    return -1;
+}
+
+const char* nlb_fcn1var_name(int fcn_id) {
+    if (fcn_id < 0 || fcn_id >= FCN1_COUNT) return nullptr;
+    return fcn1_table()[fcn_id].name;
+}
+
+int nlb_fcn1var_info(int fcn_id, int* args_len, int* has_derivative) {
+    if (fcn_id < 0 || fcn_id >= FCN1_COUNT) return NLB_ERR_UNKNOWN_FCN;
+    if (args_len) *args_len = fcn1_table()[fcn_id].args_len;
+    if (has_derivative) *has_derivative = fcn1_table()[fcn_id].has_diff;
+    return NLB_OK;
+}
+
+int nlb_brent_solve_batch(nlb_handle* h, const nlb_params_1var* params, int fcn_id, int64_t B, const double* lim1,
+                          const double* lim2, double* x, double* f, const double* args, nlb_iteration_behavior* ib,
+                          int32_t* status, void* stream) {
+    return solve_1var_batch(h, 0, params, fcn_id, B, lim1, lim2, x, f, args, ib, status, stream);
+}
+
+int nlb_newton_1var_solve_batch(nlb_handle* h, const nlb_params_1var* params, int fcn_id, int64_t B,
+                                const double* lim1, const double* lim2, double* x, double* f, const double* args,
+                                nlb_iteration_behavior* ib, int32_t* status, void* stream) {
+    return solve_1var_batch(h, 1, params, fcn_id, B, lim1, lim2, x, f, args, ib, status, stream);
 }
 
 int nlb_vecfcn_eval_batch(nlb_handle* h, int fcn_id, int64_t B, int m, int n, const double* x, double* fvec,

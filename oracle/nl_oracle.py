@@ -32,6 +32,18 @@ class Params(C.Structure):
     ]
 
 
+class Params1(C.Structure):
+    """equation_solver_1var settings (brent_solver, newton_1var_solver)."""
+
+    _fields_ = [
+        ("max_fcn_evals", C.c_int32),
+        ("fcn_tol", C.c_double),
+        ("var_tol", C.c_double),
+        ("diff_tol", C.c_double),
+        ("use_analytic_diff", C.c_int32),
+    ]
+
+
 class ClsOptions(C.Structure):
     """constrained_least_squares_solver's own settings (radius, step scaling) and the limit arrays."""
 
@@ -89,6 +101,11 @@ class Oracle:
         lib.nlo_dgesv.restype = C.c_int
         lib.nlo_cls_solve.restype = C.c_int
         lib.nlo_polyfit_batch.restype = C.c_int
+        lib.nlo_fcn1_lookup.argtypes = [C.c_char_p]
+        lib.nlo_fcn1_lookup.restype = C.c_int
+        lib.nlo_fcn1_eval.argtypes = [C.c_int, C.c_double, C.c_void_p]
+        lib.nlo_fcn1_eval.restype = C.c_double
+        lib.nlo_solve_1var_batch.restype = C.c_int
         lib.nlo_polyval_batch.restype = C.c_int
         lib.nlo_cls_solve_batch.restype = C.c_int
 
@@ -230,6 +247,46 @@ class Oracle:
                                           int(nthreads))
         if rc:
             raise RuntimeError("nlo_cls_solve_batch -> %d" % rc)
+        return x, f, ib, status
+
+    def params1(self, **kw):
+        p = Params1()
+        self.lib.nlo_params1_default(C.byref(p))
+        for k, v in kw.items():
+            if not hasattr(p, k):
+                raise AttributeError(k)
+            setattr(p, k, v)
+        return p
+
+    def fcn1_id(self, name):
+        i = self.lib.nlo_fcn1_lookup(name.encode())
+        if i < 0:
+            raise KeyError(name)
+        return i
+
+    def fcn1_info(self, fid):
+        a, d = C.c_int(), C.c_int()
+        if self.lib.nlo_fcn1_info(fid, C.byref(a), C.byref(d)) != 0:
+            raise KeyError(fid)
+        return {"args_len": a.value, "has_diff": d.value}
+
+    def solve_1var_batch(self, solver, fcn, lim1, lim2, x0=None, args=None, params=None, want_f=True, nthreads=0):
+        """solver: "brent" | "newton_1var".  lim1, lim2: (B,) limits.  Returns (x, f or None, ib, status)."""
+        fid = self.fcn1_id(fcn) if isinstance(fcn, str) else fcn
+        lim1 = np.ascontiguousarray(lim1, dtype=np.float64)
+        lim2 = np.ascontiguousarray(lim2, dtype=np.float64)
+        B = lim1.size
+        x = np.zeros(B) if x0 is None else np.array(x0, dtype=np.float64)
+        f = np.zeros(B) if want_f else None
+        ib = np.zeros(B, dtype=IB_DTYPE)
+        status = np.zeros(B, dtype=np.int32)
+        p = params or self.params1()
+        args = None if args is None else np.ascontiguousarray(args, dtype=np.float64)
+        rc = self.lib.nlo_solve_1var_batch({"brent": 0, "newton_1var": 1}[solver], fid, C.c_long(B), C.byref(p),
+                                           self._ptr(lim1), self._ptr(lim2), self._ptr(x), self._ptr(f), self._ptr(args),
+                                           self._ptr(ib), self._ptr(status), int(nthreads))
+        if rc:
+            raise RuntimeError("nlo_solve_1var_batch -> %d" % rc)
         return x, f, ib, status
 
     def polyfit_batch(self, x, y, order, thru_zero=False, nthreads=0):

@@ -17,6 +17,7 @@
 
 #include "nl_lapack.h"
 #include "nl_polynomial.h"
+#include "nl_scalar.h"
 #include "nl_solvers.h"
 
 namespace nlo {
@@ -257,6 +258,56 @@ int nlo_polyval_batch(long B, int order, int npts, int x_is_shared, const double
             real xv = x_is_shared ? R(x)[i] : R(x)[(long)i * B + b];
             R(y)[(long)i * B + b] = poly_eval(order, c.data(), xv);
         }
+    }
+    return 0;
+}
+
+// brent_solver (solver = 0) / newton_1var_solver (solver = 1) over B equations.  lim1 / lim2: the value_pair of
+// each equation; x in/out; f out, or null (= the optional argument absent); args[k*B + b].
+int nlo_fcn1_lookup(const char* name) {
+    const Problem1* p = nl_problem1_by_name(name);
+    return p ? p->id : -1;
+}
+int nlo_fcn1_info(int id, int* args_len, int* has_diff) {
+    const Problem1* p = nl_problem1(id);
+    if (!p) return -1;
+    *args_len = p->args_len; *has_diff = p->diff != nullptr;
+    return 0;
+}
+void nlo_params1_default(Params1* p) { params1_default(p); }
+double nlo_fcn1_eval(int id, double x, const double* args) { return dval(nl_problem1(id)->fcn(real(x), R(args))); }
+
+int nlo_solve_1var_batch(int solver, int fcn_id, long B, const Params1* prm, const double* lim1, const double* lim2,
+                         double* x, double* f, const double* args, IterBehavior* ib, int32_t* status, int nthreads) {
+    const Problem1* p = nl_problem1(fcn_id);
+    if (!p) return NL_UNDEFINED_FUNCTION_ERROR;
+    if (solver < 0 || solver > 1) return NL_INVALID_INPUT_ERROR;
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+    nthreads = 1;
+#endif
+#pragma omp parallel num_threads(nthreads)
+    {
+        std::vector<real> al(p->args_len > 0 ? p->args_len : 1);
+#ifdef NL_COUNT_FLOPS
+        g_flops = 0;
+#endif
+#pragma omp for schedule(dynamic, 256)
+        for (long b = 0; b < B; ++b) {
+            for (int k = 0; k < p->args_len; ++k) al[k] = R(args)[(long)k * B + b];
+            real xv = R(x)[b], fv = 0.0;
+            IterBehavior lib;
+            int st = solver == 0 ? brent_solve(p, al.data(), prm, R(lim1)[b], R(lim2)[b], &xv, &fv, &lib)
+                                 : newton1_solve(p, al.data(), prm, R(lim1)[b], R(lim2)[b], &xv, &fv, f != nullptr, &lib);
+            R(x)[b] = xv;
+            if (f) R(f)[b] = fv;
+            if (ib) ib[b] = lib;
+            if (status) status[b] = st;
+        }
+#ifdef NL_COUNT_FLOPS
+        g_flops_total += g_flops;
+#endif
     }
     return 0;
 }

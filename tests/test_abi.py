@@ -33,7 +33,8 @@ def test_every_entry_point_cites_the_reference():
                  "qns_solve, src/nonlin_solve.f90:156-425", "vfh_jac_fcn, src/nonlin_multi_eqn_mult_var.f90:198-277",
                  "vfh_fcn, src/nonlin_multi_eqn_mult_var.f90:178-195", "src/nonlin_types.f90:8-29",
                  "cls_solve, src/nonlin_least_squares.f90:938-1176", "poly_fit, src/nonlin_polynomials.f90:146-199",
-                 "poly_eval_double, src/nonlin_polynomials.f90:256-283"):
+                 "poly_eval_double, src/nonlin_polynomials.f90:256-283", "brent_solve, src/nonlin_solve.f90:643-835",
+                 "newt1var_solve,\n * src/nonlin_solve.f90:840-1032"):
         assert proc in HEADER
 
 
@@ -66,6 +67,26 @@ def test_constrained_options_struct(oracle):
     block = HEADER[HEADER.index("typedef struct nlb_constrained_options {"):HEADER.index("} nlb_constrained_options;")]
     pos = [block.index(f[0]) for f in _lib.nlb_constrained_options._fields_]
     assert pos == sorted(pos)
+
+
+def test_params_1var_struct_and_registry(oracle):
+    from nonlin_b200 import _lib
+    from oracle.nl_oracle import Params1
+
+    lib = _lib.load()
+    p = _lib.nlb_params_1var()
+    lib.nlb_params_1var_default(C.byref(p))
+    # defaults of equation_solver_1var (src/nonlin_single_var.f90:44-54)
+    assert (p.max_fcn_evals, p.fcn_tol, p.var_tol, p.diff_tol, p.use_analytic_diff) == (100, 1e-8, 1e-12, 1e-12, 0)
+    assert [f[0] for f in Params1._fields_] == [f[0] for f in _lib.nlb_params_1var._fields_]
+    assert C.sizeof(Params1) == C.sizeof(_lib.nlb_params_1var)
+    for i in range(lib.nlb_fcn1var_count()):
+        name = lib.nlb_fcn1var_name(i).decode()
+        assert oracle.fcn1_id(name) == i and lib.nlb_fcn1var_lookup(name.encode()) == i
+        a, d = C.c_int(), C.c_int()
+        assert lib.nlb_fcn1var_info(i, C.byref(a), C.byref(d)) == 0
+        assert oracle.fcn1_info(i) == {"args_len": a.value, "has_diff": d.value}
+    assert lib.nlb_fcn1var_lookup(b"nope") == -1 and lib.nlb_fcn1var_name(99) is None
 
 
 def test_params_struct_matches_oracle_struct(oracle):

@@ -69,6 +69,32 @@ def test_polynomial_object():
         p.fit(np.zeros(5), np.zeros((4, 2)), 2)
 
 
+def test_one_variable_solver_objects():
+    for cls in (nb.brent_solver, nb.newton_1var_solver):
+        s = cls()
+        assert isinstance(s, nb.equation_solver_1var)
+        assert s.get_max_fcn_evals() == 100                      # src/nonlin_single_var.f90:45
+        assert s.get_fcn_tolerance() == 1e-8                     # :47
+        assert s.get_var_tolerance() == 1e-12                    # :49
+        assert s.get_diff_tolerance() == 1e-12                   # :51
+        assert s.get_print_status() is False                     # :54
+        s.set_max_fcn_evals(7); s.set_fcn_tolerance(1e-3); s.set_var_tolerance(1e-4); s.set_diff_tolerance(1e-5)
+        assert (s.get_max_fcn_evals(), s.get_fcn_tolerance(), s.get_var_tolerance(), s.get_diff_tolerance()) == (7, 1e-3, 1e-4, 1e-5)
+    obj = nb.fcn1var_helper()
+    assert not obj.is_fcn_defined() and not obj.is_derivative_defined()
+    obj.set_fcn("cubic_wallis")
+    assert obj.is_fcn_defined() and not obj.is_derivative_defined()
+    obj.set_diff()
+    assert obj.is_derivative_defined()
+    assert "sinx_div_x" in nb.fcn1var_names()
+    lim = nb.value_pair(1.5, 5.0)                                # src/nonlin_types.f90:31-37
+    assert (lim.x1, lim.x2) == (1.5, 5.0)
+    with pytest.raises(nb.NonlinError):
+        nb.brent_solver().solve(nb.fcn1var_helper(), np.zeros(3), lim)
+    with pytest.raises(nb.NonlinError):
+        nb.brent_solver().solve(obj, np.zeros((3, 2)), lim)
+
+
 def test_quasi_newton_and_line_search_settings():
     s = nb.quasi_newton_solver()
     assert s.get_jacobian_interval() == 5                        # src/nonlin_solve.f90:51

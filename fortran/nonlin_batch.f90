@@ -16,7 +16,7 @@ module nonlin_batch
     private
     public :: nlb_engine, batch_vecfcn_helper, batch_iteration_behavior
     public :: batch_least_squares_solver, batch_newton_solver, batch_quasi_newton_solver, batch_line_search
-    public :: batch_constrained_least_squares_solver, batch_polynomial
+    public :: batch_constrained_least_squares_solver, batch_polynomial, batch_solver_1var
     public :: NLB_OK, NL_NO_ERROR, NL_CONVERGENCE_ERROR, NL_DIVERGENT_BEHAVIOR_ERROR, &
         NL_SPURIOUS_CONVERGENCE_ERROR
 
@@ -33,6 +33,13 @@ module nonlin_batch
         integer(c_int32_t) :: jacobian_interval, use_line_search, ls_max_fcn_evals
         real(c_double) :: ls_alpha, ls_factor
         integer(c_int32_t) :: use_analytic_jacobian, max_iter_guard
+    end type
+
+    !> struct nlb_params_1var
+    type, bind(C) :: nlb_params_1var
+        integer(c_int32_t) :: max_fcn_evals
+        real(c_double) :: fcn_tol, var_tol, diff_tol
+        integer(c_int32_t) :: use_analytic_diff
     end type
 
     !> struct nlb_constrained_options (lower / upper: c_loc of n host doubles, or c_null_ptr)
@@ -99,6 +106,32 @@ module nonlin_batch
             integer(c_int64_t), value :: b
             integer(c_int), value :: order, npts, x_is_shared
             type(c_ptr), value :: coeffs, x, y, stream
+        end function
+        subroutine nlb_params_1var_default(p) bind(C, name = "nlb_params_1var_default")
+            import :: nlb_params_1var
+            type(nlb_params_1var), intent(out) :: p
+        end subroutine
+        integer(c_int) function nlb_fcn1var_lookup(name) bind(C, name = "nlb_fcn1var_lookup")
+            import :: c_char, c_int
+            character(kind = c_char), dimension(*), intent(in) :: name
+        end function
+        integer(c_int) function nlb_brent_solve_batch(handle, params, fcn_id, b, lim1, lim2, x, f, args, ib, &
+                status, stream) bind(C, name = "nlb_brent_solve_batch")
+            import :: c_ptr, c_int, c_int64_t, nlb_params_1var
+            type(c_ptr), value :: handle
+            type(nlb_params_1var), intent(in) :: params
+            integer(c_int), value :: fcn_id
+            integer(c_int64_t), value :: b
+            type(c_ptr), value :: lim1, lim2, x, f, args, ib, status, stream
+        end function
+        integer(c_int) function nlb_newton_1var_solve_batch(handle, params, fcn_id, b, lim1, lim2, x, f, args, ib, &
+                status, stream) bind(C, name = "nlb_newton_1var_solve_batch")
+            import :: c_ptr, c_int, c_int64_t, nlb_params_1var
+            type(c_ptr), value :: handle
+            type(nlb_params_1var), intent(in) :: params
+            integer(c_int), value :: fcn_id
+            integer(c_int64_t), value :: b
+            type(c_ptr), value :: lim1, lim2, x, f, args, ib, status, stream
         end function
         integer(c_int) function nlb_newton_solve_batch(handle, params, fcn_id, b, m, n, x, fvec, sys, &
                 shared, ib, status, stream) bind(C, name = "nlb_newton_solve_batch")
@@ -202,6 +235,20 @@ module nonlin_batch
         procedure, public :: set_trust_region_radius => bcls_set_radius
         procedure, public :: set_step_scaling_factor => bcls_set_factor
         procedure, public :: solve_batch => cls_solve_batch
+    end type
+
+    !> brent_solver / newton_1var_solver (nonlin_solve.f90:69-85) over B equations: m_newton selects the method
+    type :: batch_solver_1var
+        integer(int32) :: m_maxEval = 100
+        real(real64) :: m_fcnTol = 1.0d-8
+        real(real64) :: m_xtol = 1.0d-12
+        real(real64) :: m_difftol = 1.0d-12
+        logical :: m_newton = .false.
+        logical :: m_useDiff = .false.
+        integer(c_int) :: m_fcn = -1
+    contains
+        procedure, public :: set_fcn => bs1_set_fcn
+        procedure, public :: solve_batch => bs1_solve_batch
     end type
 
     !> polynomial (nonlin_polynomials.f90:20-71) for B data sets: coefficients c(B, order + 1), c(:,1) = c0
@@ -464,6 +511,43 @@ contains
         ierr = nlb_constrained_least_squares_solve_batch(eng%handle, p, o, fcn%m_fcn, int(size(x, 1), c_int64_t), &
             int(fcn%m_nfcn, c_int), int(fcn%m_nvar, c_int), c_loc(x), c_loc(fvec), pa, ps, c_loc(ib), &
             c_loc(status), c_null_ptr)
+    end subroutine
+
+    subroutine bs1_set_fcn(this, name)
+        class(batch_solver_1var), intent(inout) :: this
+        character(len = *), intent(in) :: name
+        this%m_fcn = nlb_fcn1var_lookup(trim(name) // c_null_char)
+    end subroutine
+
+    !> `call solver%solve(fcn, x, lim, f, ib, args)` for B equations: lim1(B), lim2(B) = the value_pair of each
+    !! equation, x(B) in/out, f(B) out, args(B, args_len) optional.
+    subroutine bs1_solve_batch(this, eng, lim1, lim2, x, f, ib, status, ierr, args)
+        class(batch_solver_1var), intent(in) :: this
+        type(nlb_engine), intent(in) :: eng
+        real(real64), intent(in), dimension(:), contiguous, target :: lim1, lim2
+        real(real64), intent(inout), dimension(:), contiguous, target :: x
+        real(real64), intent(out), dimension(:), contiguous, target :: f
+        type(batch_iteration_behavior), intent(out), dimension(:), target :: ib
+        integer(int32), intent(out), dimension(:), target :: status
+        integer, intent(out) :: ierr
+        real(real64), intent(in), dimension(:,:), contiguous, target, optional :: args
+        type(nlb_params_1var) :: p
+        type(c_ptr) :: pa
+        call nlb_params_1var_default(p)
+        p%max_fcn_evals = this%m_maxEval
+        p%fcn_tol = this%m_fcnTol
+        p%var_tol = this%m_xtol
+        p%diff_tol = this%m_difftol
+        p%use_analytic_diff = merge(1_c_int32_t, 0_c_int32_t, this%m_useDiff)
+        pa = c_null_ptr
+        if (present(args)) pa = c_loc(args)
+        if (this%m_newton) then
+            ierr = nlb_newton_1var_solve_batch(eng%handle, p, this%m_fcn, int(size(x), c_int64_t), c_loc(lim1), &
+                c_loc(lim2), c_loc(x), c_loc(f), pa, c_loc(ib), c_loc(status), c_null_ptr)
+        else
+            ierr = nlb_brent_solve_batch(eng%handle, p, this%m_fcn, int(size(x), c_int64_t), c_loc(lim1), &
+                c_loc(lim2), c_loc(x), c_loc(f), pa, c_loc(ib), c_loc(status), c_null_ptr)
+        end if
     end subroutine
 
     pure function bp_order(this) result(n)

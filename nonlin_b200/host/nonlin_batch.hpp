@@ -201,6 +201,76 @@ protected:
     }
 };
 
+// reference src/nonlin_types.f90:31-37 — search limits of the one-variable solvers, one pair per equation
+struct value_pair_batch {
+    const double* x1;
+    const double* x2;
+};
+
+// reference src/nonlin_single_var.f90:25-41
+class fcn1var_helper {
+public:
+    void set_fcn(const std::string& registered_name) {
+        id_ = nlb_fcn1var_lookup(registered_name.c_str());
+        if (id_ < 0) throw error(NLB_ERR_UNKNOWN_FCN, "one-variable function '" + registered_name + "' is not registered");
+        diff_ = false;
+    }
+    void set_diff(bool use_registered = true) { diff_ = use_registered; }
+    bool is_fcn_defined() const { return id_ >= 0; }
+    bool is_derivative_defined() const { return diff_; }
+    int id() const { return id_; }
+private:
+    int id_ = -1;
+    bool diff_ = false;
+};
+
+// reference src/nonlin_single_var.f90:43-69
+class equation_solver_1var {
+public:
+    virtual ~equation_solver_1var() = default;
+    int get_max_fcn_evals() const { return p_.max_fcn_evals; }
+    void set_max_fcn_evals(int n) { p_.max_fcn_evals = n; }
+    double get_fcn_tolerance() const { return p_.fcn_tol; }
+    void set_fcn_tolerance(double x) { p_.fcn_tol = x; }
+    double get_var_tolerance() const { return p_.var_tol; }
+    void set_var_tolerance(double x) { p_.var_tol = x; }
+    double get_diff_tolerance() const { return p_.diff_tol; }
+    void set_diff_tolerance(double x) { p_.diff_tol = x; }
+    // `call solver%solve(fcn, x, lim, f, ib, args)` over B equations; f may be null (optional argument absent)
+    void solve(const engine& eng, const fcn1var_helper& fcn, int64_t B, double* x, const value_pair_batch& lim,
+               double* f = nullptr, iteration_behavior* ib = nullptr, int32_t* status = nullptr,
+               const double* args = nullptr, void* stream = nullptr) {
+        if (!fcn.is_fcn_defined()) throw error(NLB_ERR_UNKNOWN_FCN, "no function set (NL_UNDEFINED_FUNCTION_ERROR)");
+        nlb_params_1var p = p_;
+        p.use_analytic_diff = fcn.is_derivative_defined();
+        eng.check(launch(eng.get(), p, fcn.id(), B, lim.x1, lim.x2, x, f, args, ib, status, stream));
+    }
+protected:
+    equation_solver_1var() { nlb_params_1var_default(&p_); }
+    virtual int launch(nlb_handle* h, const nlb_params_1var& p, int id, int64_t B, const double* l1, const double* l2,
+                       double* x, double* f, const double* args, iteration_behavior* ib, int32_t* status,
+                       void* stream) = 0;
+    nlb_params_1var p_;
+};
+
+// reference src/nonlin_solve.f90:69-76
+class brent_solver : public equation_solver_1var {
+protected:
+    int launch(nlb_handle* h, const nlb_params_1var& p, int id, int64_t B, const double* l1, const double* l2, double* x,
+               double* f, const double* args, iteration_behavior* ib, int32_t* status, void* stream) override {
+        return nlb_brent_solve_batch(h, &p, id, B, l1, l2, x, f, args, ib, status, stream);
+    }
+};
+
+// reference src/nonlin_solve.f90:78-85
+class newton_1var_solver : public equation_solver_1var {
+protected:
+    int launch(nlb_handle* h, const nlb_params_1var& p, int id, int64_t B, const double* l1, const double* l2, double* x,
+               double* f, const double* args, iteration_behavior* ib, int32_t* status, void* stream) override {
+        return nlb_newton_1var_solve_batch(h, &p, id, B, l1, l2, x, f, args, ib, status, stream);
+    }
+};
+
 // reference src/nonlin_polynomials.f90:20-71 — a batch of B polynomials of one order; coefficients
 // c[k*B + b], k = 0..order (get(i) of the reference is row i - 1).  Host buffers.
 class polynomial {

@@ -63,6 +63,24 @@ int main() {
                 return 1;
             }
         }
+        // test_brent_1 / test_newton_1var_1 (tests/nonlin_test_solve.f90:729, :898): sin(x)/x on [1.5, 5] -> pi
+        {
+            nonlin::fcn1var_helper f1;
+            f1.set_fcn("sinx_div_x");
+            std::vector<double> l1(B, 1.5), l2(B, 5.0), xr(B), fr(B);
+            nonlin::brent_solver brent;
+            nonlin::newton_1var_solver newt;
+            for (int which = 0; which < 2; ++which) {
+                nonlin::value_pair_batch lim{l1.data(), l2.data()};
+                if (which == 0) brent.solve(eng, f1, B, xr.data(), lim, fr.data(), ibc.data(), statusc.data());
+                else newt.solve(eng, f1, B, xr.data(), lim, fr.data(), ibc.data(), statusc.data());
+                const double d = xr[B / 2] - 3.141592653589793;
+                if (statusc[B / 2] != 0 || d > 1e-6 || d < -1e-6) {
+                    std::printf("FAIL (one-variable solver %d) x = %.12f\n", which, xr[B / 2]);
+                    return 1;
+                }
+            }
+        }
         std::printf("Solution: (%.5f, %.5f)\nResidual: (%.3e, %.3e)\nIterations: %d\nFunction Evaluations: %d\nJacobian Evaluations: %d\n",
                     x[0], x[B], f[0], f[B], ib[0].iter_count, ib[0].fcn_count, ib[0].jacobian_count);
     } catch (const nonlin::error& e) {

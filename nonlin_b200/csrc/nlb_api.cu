@@ -170,37 +170,14 @@ tps_solve_kernel(DevParams p, long long nsys, long long B, double* __restrict__ 
     if (status) status[b] = st.status;
 }
 
-// constrained_least_squares_solver: same mapping, the limits and the radius travel by value.
+// constrained_least_squares_solver: persistent thread-per-system kernel (tps_cls_refill); the limits and the radius
+// travel by value.
 template <class F>
 __global__ void __launch_bounds__(TPS_BLOCK)
-tps_cls_kernel(DevParams p, DevCls o, long long nsys, long long B, double* __restrict__ x, double* __restrict__ fvec,
-               const double* __restrict__ sys, const double* __restrict__ shared,
+tps_cls_kernel(DevParams p, DevCls o, long long nsys, long long B, unsigned long long* cursor, double* __restrict__ x,
+               double* __restrict__ fvec, const double* __restrict__ sys, const double* __restrict__ shared,
                nlb_iteration_behavior* __restrict__ ib, int32_t* __restrict__ status) {
-    constexpr int M = F::M, N = F::N;
-    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (b >= nsys) return;
-    double xl[N], fl[M];
-#pragma unroll
-    for (int j = 0; j < N; ++j) xl[j] = x[j * B + b];
-    SysCtx c{sys ? sys + b : nullptr, shared, B, M, N};
-    SolveStats st;
-    tps_cls_solve<F>(p, o, c, xl, fl, st);
-#pragma unroll
-    for (int j = 0; j < N; ++j) x[j * B + b] = xl[j];
-#pragma unroll(M <= 8 ? M : 1)
-    for (int i = 0; i < M; ++i) fvec[i * B + b] = fl[i];
-    if (ib) {
-        nlb_iteration_behavior o2;
-        o2.iter_count = st.iter;
-        o2.fcn_count = st.nfev;
-        o2.jacobian_count = st.njac;
-        o2.gradient_count = 0;
-        o2.converge_on_fcn = st.cf;
-        o2.converge_on_chng = st.cx;
-        o2.converge_on_zero_diff = st.cg;
-        ib[b] = o2;
-    }
-    if (status) status[b] = st.status;
+    tps_cls_refill<F>(p, o, nsys, B, cursor, x, fvec, sys, shared, ib, status);
 }
 
 // Persistent variant for Newton: grid = resident CTAs only, lanes pull systems from a cursor.
@@ -405,23 +382,36 @@ int dispatch_tps(nlb_handle* h, int fcn_id, const DevParams& p, long long nsys, 
     }
 }
 
+template <class F>
+int launch_cls(nlb_handle* h, const DevParams& p, const DevCls& o, long long nsys, long long B, double* x, double* fvec,
+               const double* sys, const double* shared, nlb_iteration_behavior* ib, int32_t* status, cudaStream_t s) {
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+        NLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, tps_cls_kernel<F>, TPS_BLOCK, 0));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
+    long long grid = (nsys + TPS_BLOCK - 1) / TPS_BLOCK;
+    const long long resident = (long long)h->num_sms * ctas_per_sm;
+    if (grid > resident) grid = resident;
+    unsigned long long* cursor = h->dcursor + (h->cursor_next++ & 15u);
+    NLB_CUDA(h, cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), s));
+    tps_cls_kernel<F><<<(unsigned)grid, TPS_BLOCK, 0, s>>>(p, o, nsys, B, cursor, x, fvec, sys, shared, ib, status);
+    ++h->launches;
+    NLB_CUDA(h, cudaGetLastError());
+    return NLB_OK;
+}
+
 int dispatch_cls(nlb_handle* h, int fcn_id, const DevParams& p, const DevCls& o, long long nsys, long long B, double* x,
                  double* fvec, const double* sys, const double* shared, nlb_iteration_behavior* ib, int32_t* status,
                  cudaStream_t s) {
     if (nsys == 0) return NLB_OK;
-    const unsigned grid = (unsigned)((nsys + TPS_BLOCK - 1) / TPS_BLOCK);
     switch (fcn_id) {
-#define X(F)                                                                                                  \
-    case F::ID:                                                                                               \
-        tps_cls_kernel<F><<<grid, TPS_BLOCK, 0, s>>>(p, o, nsys, B, x, fvec, sys, shared, ib, status);        \
-        break;
+#define X(F) \
+    case F::ID: return launch_cls<F>(h, p, o, nsys, B, x, fvec, sys, shared, ib, status, s);
         NLB_FIXED_FCNS(X)
 #undef X
         default: return set_err(h, NLB_ERR_UNSUPPORTED, "no constrained least-squares kernel for this residual");
     }
-    ++h->launches;
-    NLB_CUDA(h, cudaGetLastError());
-    return NLB_OK;
 }
 
 int ensure_device(nlb_handle* h);

@@ -367,105 +367,186 @@ NLB_DEV void dogleg(double delta, const double (&x)[N], const double (&f)[M], co
     prered = -c1 - c2;
 }
 
+// State of one constrained solve between outer iterations.
 template <class F>
-NLB_DEV void tps_cls_solve(const DevParams& prm, const DevCls& o, const SysCtx& c, double (&x)[F::N],
-                           double (&fvec)[F::M], SolveStats& st) {
+struct ClsState {
+    double x[F::N], fvec[F::M];
+    double fnorm, delta;
+    int iter, neval, njac;
+    bool xcnvrg, fcnvrg, gcnvrg, converged;
+};
+
+// Everything before the outer loop (:1038-1049).  Returns false when the solve ends here: the start, after clamping
+// to the limits, or the first residual is not finite - the reference returns without an error and ib stays zero.
+template <class F>
+NLB_DEV bool cls_begin(const DevCls& o, const SysCtx& c, ClsState<F>& s) {
     constexpr int M = F::M, N = F::N;
     static_assert(N <= CLS_MAX_N, "limit arrays are passed by value");
+    s.xcnvrg = s.fcnvrg = s.gcnvrg = s.converged = false;
+    s.iter = 0; s.neval = 0; s.njac = 0;
+    apply_limits(s.x, o);
+    F::eval(s.x, s.fvec, c);
+    s.fnorm = cls_norm2_m<M>(s.fvec);
+    if (!is_finite_array(s.x) || !is_finite_array(s.fvec)) { s.converged = true; return false; }
+    s.neval = 1;
+    s.delta = o.radius;
+    s.iter = 1;
+    return true;
+}
+
+// One trip of the outer loop (:1051-1160).  Returns true when the solve is over (converged or failed).
+template <class F>
+NLB_DEV bool cls_iterate(const DevParams& prm, const DevCls& o, const SysCtx& c, ClsState<F>& s) {
+    constexpr int M = F::M, N = F::N;
     const double delta_max = 1.0e3, eta = 1.0e-1, ls_cl = 1.0e-4, ls_beta = 0.5;
     const int ls_max_iter = 10;
-    bool converged = false, xcnvrg = false, fcnvrg = false, gcnvrg = false;
-    int neval = 0, iter = 0, njac = 0;
+    double (&x)[N] = s.x;
+    double (&fvec)[M] = s.fvec;
+    double jac[M * N], qr[M * N], tau[N], sc[N], g[N], p[N], xnew[N], Jp[M], fnew[M];
 
-    apply_limits(x, o);
-    F::eval(x, fvec, c);
-    neval = 1;
-    double fnorm = cls_norm2_m<M>(fvec);
-    if (!is_finite_array(x) || !is_finite_array(fvec)) return;      // :1043-1045, ib stays zero, no error
-
-    double jac[M * N], qr[M * N], tau[N], s[N], g[N], p[N], xnew[N], Jp[M], fnew[M];
-    double delta = o.radius;
-    iter = 1;
-    for (;;) {
-        fd_jacobian<F>(x, jac, fvec, fnew, c, prm.use_analytic_jacobian != 0);
-        ++njac;
+    fd_jacobian<F>(x, jac, fvec, fnew, c, prm.use_analytic_jacobian != 0);
+    ++s.njac;
 #pragma unroll(M * N <= 16 ? M * N : 1)
-        for (int e = 0; e < M * N; ++e) qr[e] = jac[e];
-        cls_qr_factor<M, N>(qr, tau);
-        coleman_li_scaling(x, o, s);
-        double prered;
-        dogleg<M, N>(delta, x, fvec, jac, qr, tau, s, o, p, g, Jp, prered);
-        const double xnorm = scaled_norm(p, s);
-        const double gnorm = norm2_vec(g);
+    for (int e = 0; e < M * N; ++e) qr[e] = jac[e];
+    cls_qr_factor<M, N>(qr, tau);
+    coleman_li_scaling(x, o, sc);
+    double prered;
+    dogleg<M, N>(s.delta, x, fvec, jac, qr, tau, sc, o, p, g, Jp, prered);
+    const double xnorm = scaled_norm(p, sc);
+    const double gnorm = norm2_vec(g);
 #pragma unroll
-        for (int i = 0; i < N; ++i) xnew[i] = x[i] + p[i];
+    for (int i = 0; i < N; ++i) xnew[i] = x[i] + p[i];
 
-        F::eval(xnew, fnew, c);
-        double fnewnorm = cls_norm2_m<M>(fnew);
-        ++neval;
+    F::eval(xnew, fnew, c);
+    double fnewnorm = cls_norm2_m<M>(fnew);
+    ++s.neval;
 
-        const double actred = 0.5 * (fnorm * fnorm - fnewnorm * fnewnorm);
-        double rho;
-        if (prered > 0.0 && actred >= 0.0) rho = actred / prered;
-        else rho = 0.0;
+    const double actred = 0.5 * (s.fnorm * s.fnorm - fnewnorm * fnewnorm);
+    double rho;
+    if (prered > 0.0 && actred >= 0.0) rho = actred / prered;
+    else rho = 0.0;
 
-        if (rho < 0.25) {
-            delta = nl_max(0.25, 1.0e-12);
-        } else if (rho > 0.75 && fabs(xnorm - delta) < 1.0e-12 * delta) {
-            delta = nl_min(2.0 * delta, delta_max);
-        }
-
-        if (rho > eta && fnewnorm <= fnorm) {
-#pragma unroll
-            for (int i = 0; i < N; ++i) x[i] = xnew[i];
-            apply_limits(x, o);
-            NLB_CLS_UNROLL_M
-            for (int i = 0; i < M; ++i) fvec[i] = fnew[i];
-            fnorm = fnewnorm;
-            ++iter;
-        } else {
-            const double dderiv = dot_vec(g, p);
-            if (dderiv >= 0.0) {
-                delta = nl_max(0.5 * delta, 1.0e-12);
-            } else {
-                double stepscale = o.scaling;
-                bool accepted = false;
-                for (int k = 1; k <= ls_max_iter; ++k) {
-#pragma unroll
-                    for (int i = 0; i < N; ++i) xnew[i] = x[i] + stepscale * p[i];
-                    apply_limits(xnew, o);
-                    F::eval(xnew, fnew, c);
-                    ++neval;
-                    fnewnorm = cls_norm2_m<M>(fnew);
-                    if (fnewnorm <= fnorm + ls_cl * stepscale * dderiv) {
-#pragma unroll
-                        for (int i = 0; i < N; ++i) x[i] = xnew[i];
-                        NLB_CLS_UNROLL_M
-                        for (int i = 0; i < M; ++i) fvec[i] = fnew[i];
-                        fnorm = fnewnorm;
-                        ++iter;
-                        delta = nl_max(stepscale * xnorm, 1.0e-12);
-                        accepted = true;
-                        break;
-                    }
-                    stepscale = stepscale * ls_beta;
-                }
-                if (!accepted) delta = nl_max(0.5 * delta, 1.0e-12);
-            }
-        }
-
-        if (!is_finite_array(x) || !is_finite_array(fvec)) break;
-
-        if (xnorm <= prm.var_tol) { converged = true; xcnvrg = true; break; }
-        if (fabs(actred) <= prm.fcn_tol && fabs(prered) <= prm.fcn_tol && 0.5 * rho <= 1.0) {
-            converged = true; fcnvrg = true; break;
-        }
-        if (gnorm <= prm.grad_tol) { converged = true; gcnvrg = true; break; }
-        if (neval >= prm.max_fcn_evals) break;
+    if (rho < 0.25) {
+        s.delta = nl_max(0.25, 1.0e-12);
+    } else if (rho > 0.75 && fabs(xnorm - s.delta) < 1.0e-12 * s.delta) {
+        s.delta = nl_min(2.0 * s.delta, delta_max);
     }
-    st.iter = iter; st.nfev = neval; st.njac = njac;
-    st.cf = fcnvrg; st.cx = xcnvrg; st.cg = gcnvrg;
-    st.status = converged ? 0 : NLB_CONVERGENCE_ERROR;
+
+    if (rho > eta && fnewnorm <= s.fnorm) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = xnew[i];
+        apply_limits(x, o);
+        NLB_CLS_UNROLL_M
+        for (int i = 0; i < M; ++i) fvec[i] = fnew[i];
+        s.fnorm = fnewnorm;
+        ++s.iter;
+    } else {
+        const double dderiv = dot_vec(g, p);
+        if (dderiv >= 0.0) {
+            s.delta = nl_max(0.5 * s.delta, 1.0e-12);
+        } else {
+            double stepscale = o.scaling;
+            bool accepted = false;
+            for (int k = 1; k <= ls_max_iter; ++k) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) xnew[i] = x[i] + stepscale * p[i];
+                apply_limits(xnew, o);
+                F::eval(xnew, fnew, c);
+                ++s.neval;
+                fnewnorm = cls_norm2_m<M>(fnew);
+                if (fnewnorm <= s.fnorm + ls_cl * stepscale * dderiv) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) x[i] = xnew[i];
+                    NLB_CLS_UNROLL_M
+                    for (int i = 0; i < M; ++i) fvec[i] = fnew[i];
+                    s.fnorm = fnewnorm;
+                    ++s.iter;
+                    s.delta = nl_max(stepscale * xnorm, 1.0e-12);
+                    accepted = true;
+                    break;
+                }
+                stepscale = stepscale * ls_beta;
+            }
+            if (!accepted) s.delta = nl_max(0.5 * s.delta, 1.0e-12);
+        }
+    }
+
+    if (!is_finite_array(x) || !is_finite_array(fvec)) return true;
+
+    if (xnorm <= prm.var_tol) { s.converged = true; s.xcnvrg = true; return true; }
+    if (fabs(actred) <= prm.fcn_tol && fabs(prered) <= prm.fcn_tol && 0.5 * rho <= 1.0) {
+        s.converged = true; s.fcnvrg = true; return true;
+    }
+    if (gnorm <= prm.grad_tol) { s.converged = true; s.gcnvrg = true; return true; }
+    return s.neval >= prm.max_fcn_evals;
+}
+
+template <class F>
+NLB_DEV void cls_store(const ClsState<F>& s, long long B, long long b, double* __restrict__ xg, double* __restrict__ fg,
+                       nlb_iteration_behavior* __restrict__ ibg, int32_t* __restrict__ statusg) {
+    constexpr int M = F::M, N = F::N;
+#pragma unroll
+    for (int j = 0; j < N; ++j) xg[j * B + b] = s.x[j];
+    NLB_CLS_UNROLL_M
+    for (int i = 0; i < M; ++i) fg[i * B + b] = s.fvec[i];
+    if (ibg) {
+        nlb_iteration_behavior o;
+        o.iter_count = s.iter;
+        o.fcn_count = s.neval;
+        o.jacobian_count = s.njac;
+        o.gradient_count = 0;
+        o.converge_on_fcn = s.fcnvrg;
+        o.converge_on_chng = s.xcnvrg;
+        o.converge_on_zero_diff = s.gcnvrg;
+        ibg[b] = o;
+    }
+    if (statusg) statusg[b] = s.converged ? 0 : NLB_CONVERGENCE_ERROR;
+}
+
+// Persistent form: the grid holds only resident CTAs; one trip of the loop is ONE outer iteration of whatever
+// system the lane holds, and a lane whose system ends stores it and pulls the next index from a global cursor
+// (tps_fetch: one atomic per warp).  The spread of iteration counts between systems (2...17 on the 2x2 box
+// problem) then no longer idles lanes; the warp re-converges at the top of every trip.  Same arithmetic per system.
+NLB_DEV long long cls_fetch(unsigned long long* cursor) {
+    const unsigned mask = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(cursor, (unsigned long long)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return (long long)(base + __popc(mask & ((1u << lane) - 1u)));
+}
+
+template <class F>
+NLB_DEV void tps_cls_refill(const DevParams& prm, const DevCls& o, long long nsys, long long B,
+                            unsigned long long* cursor, double* __restrict__ xg, double* __restrict__ fg,
+                            const double* __restrict__ sys, const double* __restrict__ shared,
+                            nlb_iteration_behavior* __restrict__ ibg, int32_t* __restrict__ statusg) {
+    constexpr int M = F::M, N = F::N;
+    ClsState<F> s;
+    long long b = -1;
+    bool active = false, more = true;
+    for (;;) {
+        bool finished = false;
+        if (!active && more) {
+            b = cls_fetch(cursor);
+            if (b >= nsys) more = false;
+        }
+        if (!active && more) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) s.x[j] = xg[j * B + b];
+            const SysCtx c{sys ? sys + b : nullptr, shared, B, M, N};
+            if (cls_begin<F>(o, c, s)) active = true;
+            else finished = true;
+        }
+        __syncwarp();
+        if (!__any_sync(0xffffffffu, active || finished || more)) break;
+        if (active) {
+            const SysCtx c{sys ? sys + b : nullptr, shared, B, M, N};
+            if (cls_iterate<F>(prm, o, c, s)) { finished = true; active = false; }
+        }
+        if (finished) cls_store<F>(s, B, b, xg, fg, ibg, statusg);
+    }
 }
 
 }  // namespace nlb

@@ -36,13 +36,32 @@ struct SolveStats {
 
 // Forward-difference Jacobian.  h = sqrt(eps)*|x_j| (sqrt(eps) if that is zero); divide by the
 // nominal h; columns in order j = 1..n; the caller's f(x) is reused.
-template <class F>
-NLB_DEV void fd_jacobian(double (&x)[F::N], double (&jac)[F::M * F::N], const double (&fv)[F::M],
+// Matrix stored one element every STRIDE doubles: a thread's slice of a [element][thread] shared-memory tile
+// (conflict-free: consecutive lanes hold consecutive doubles).  Indexable like a per-thread array.
+template <int STRIDE>
+struct StridedMat {
+    double* p;
+    NLB_DEV double& operator[](int e) const { return p[e * STRIDE]; }
+};
+
+template <class F, int K>
+NLB_DEV void analytic_jacobian(const double (&x)[F::N], double (&jac)[K], const SysCtx& c) {
+    F::jac(x, JacView<F::M>{jac}, c);
+}
+template <class F, int STRIDE>
+NLB_DEV void analytic_jacobian(const double (&)[F::N], const StridedMat<STRIDE>&, const SysCtx&) {
+    static_assert(!F::HAS_JAC, "registered Jacobians write per-thread arrays");
+}
+
+template <class F, class A>
+NLB_DEV void fd_jacobian(double (&x)[F::N], A& jac, const double (&fv)[F::M],
                          double (&wrk)[F::M], const SysCtx& c, bool analytic) {
     constexpr int M = F::M, N = F::N;
-    if (F::HAS_JAC && analytic) {
-        F::jac(x, JacView<M>{jac}, c);
-        return;
+    if constexpr (F::HAS_JAC) {
+        if (analytic) {
+            analytic_jacobian<F>(x, jac, c);
+            return;
+        }
     }
     const double eps = 0x1p-26;   // sqrt(epsilon(1d0))
 #pragma unroll

@@ -20,8 +20,8 @@ namespace nlb {
 #define NLB_UNROLL_M _Pragma("unroll(M <= 8 ? M : 1)")
 
 // Pivoted Householder QR in place (MINPACK QRFAC lineage).  ipvt is 0-based.
-template <int M, int N>
-NLB_DEV void lm_factor(double (&a)[M * N], int (&ipvt)[N], double (&rdiag)[N], double (&acnorm)[N], double (&wa)[N]) {
+template <int M, int N, class A>
+NLB_DEV void lm_factor(A& a, int (&ipvt)[N], double (&rdiag)[N], double (&acnorm)[N], double (&wa)[N]) {
     constexpr int MINMN = M < N ? M : N;
     const double epsmch = 0x1p-52;
 #pragma unroll
@@ -104,8 +104,8 @@ NLB_DEV void lm_factor(double (&a)[M * N], int (&ipvt)[N], double (&rdiag)[N], d
 // lineage).  r = leading N x N block of the factored Jacobian `a` (leading dimension M); the
 // strict lower triangle is overwritten with S^T, the upper triangle and diagonal are kept.
 // `wa` is the caller's work vector: only its first N entries are touched.
-template <int M, int N, int WN>
-NLB_DEV void lm_qrsolve(double (&a)[M * N], const int (&ipvt)[N], const double (&diag)[N], const double (&qtb)[N],
+template <int M, int N, int WN, class A>
+NLB_DEV void lm_qrsolve(A& a, const int (&ipvt)[N], const double (&diag)[N], const double (&qtb)[N],
                         double (&x)[N], double (&sdiag)[N], double (&wa)[WN]) {
 #pragma unroll
     for (int j = 0; j < N; ++j) {
@@ -175,8 +175,8 @@ NLB_DEV void lm_qrsolve(double (&a)[M * N], const int (&ipvt)[N], const double (
 // the Newton correction subtracts r(1:n,j)*temp from the WHOLE vector (:552), and inside the
 // iteration dxnorm is the norm of all M entries of the work array (:531), whose tail
 // n+1..m still holds Q^T f (first pass of an outer iteration) or the last trial residual.
-template <int M, int N>
-NLB_DEV void lm_par(double (&a)[M * N], const int (&ipvt)[N], const double (&diag)[N], const double (&qtb)[N],
+template <int M, int N, class A>
+NLB_DEV void lm_par(A& a, const int (&ipvt)[N], const double (&diag)[N], const double (&qtb)[N],
                     double delta, double& par, double (&x)[N], double (&sdiag)[N], double (&wa1)[N],
                     double (&wa2)[M]) {
     const double dwarf = 0x1p-1022;
@@ -291,9 +291,11 @@ NLB_DEV void lm_par(double (&a)[M * N], const int (&ipvt)[N], const double (&dia
     }
 }
 
-template <class F>
+// `jac` is the caller's storage for the m x n Jacobian / its QR factors: a per-thread array (registers or local
+// memory) or a StridedMat view of shared memory - anything indexable as jac[i + j * M].
+template <class F, class A>
 NLB_DEV void tps_lm_solve(const DevParams& p, const SysCtx& c, double (&x)[F::N], double (&fvec)[F::M],
-                          SolveStats& st) {
+                          SolveStats& st, A& jac) {
     constexpr int M = F::M, N = F::N;
     static_assert(M >= N, "least squares needs m >= n (src/nonlin_least_squares.f90:189)");
     const double eps = 0x1p-52;
@@ -303,7 +305,6 @@ NLB_DEV void tps_lm_solve(const DevParams& p, const SysCtx& c, double (&x)[F::N]
     bool xcnvrg = false, fcnvrg = false, gcnvrg = false;
     int flag = 0;
 
-    double jac[M * N];
     double wa4[M];
     double diag[N], qtf[N], wa1[N], wa2[N], wa3[N];
     int jpvt[N];
@@ -458,6 +459,13 @@ NLB_DEV void tps_lm_solve(const DevParams& p, const SysCtx& c, double (&x)[F::N]
     st.cg = gcnvrg;
     // every non-zero flag ends in `error stop NL_CONVERGENCE_ERROR` (:388-390)
     st.status = flag != 0 ? NLB_CONVERGENCE_ERROR : NLB_NO_ERROR;
+}
+
+template <class F>
+NLB_DEV void tps_lm_solve(const DevParams& p, const SysCtx& c, double (&x)[F::N], double (&fvec)[F::M],
+                          SolveStats& st) {
+    double jac[F::M * F::N];
+    tps_lm_solve<F>(p, c, x, fvec, st, jac);
 }
 
 }  // namespace nlb

@@ -743,3 +743,29 @@ def test_cls_unsupported_residual_is_an_api_error(engine):
     with pytest.raises(nb.NonlinError) as e:
         nb.constrained_least_squares_solver().solve(obj, np.ones((4, 8)), args=np.ones((64, 8)))
     assert e.value.code == nb.NLB_ERR_UNSUPPORTED
+
+
+def test_lm_shared_memory_jacobian_variant_is_bit_identical(engine):
+    """tps_lm_smem_kernel (NLB_LM_SMEM=1, an experiment kept selectable - DESIGN.md 4.1) must give the committed
+    golden bits of C1 too.  Run in a child process: the knob is read once per process."""
+    import subprocess
+    import sys
+
+    code = (
+        "import os, sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "import nonlin_b200 as nb\n"
+        "from nonlin_b200 import workloads as W\n"
+        "g = np.load(%r)\n"
+        "B = g['C1_status'].shape[0]\n"
+        "w = W.WORKLOADS['C1'](B)\n"
+        "obj = nb.vecfcn_helper(); obj.set_fcn(w['fcn'], w['m'], w['n'])\n"
+        "x = w['x0'].copy(); f = np.zeros((w['m'], B)); ib = nb.iteration_behavior(B)\n"
+        "st = nb.least_squares_solver().solve(obj, x, f, ib, args=w['args'])\n"
+        "ok = (np.array_equal(x, g['C1_x']) and np.array_equal(f, g['C1_f'])\n"
+        "      and np.array_equal(ib.view(np.int32).reshape(B, 7), g['C1_ib']) and np.array_equal(st, g['C1_status']))\n"
+        "print('SMEM_OK' if ok else 'SMEM_MISMATCH')\n"
+    ) % (os.path.dirname(HERE), os.path.join(HERE, "golden", "oracle_batches.npz"))
+    env = dict(os.environ, NLB_LM_SMEM="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert "SMEM_OK" in r.stdout, r.stdout + r.stderr

@@ -377,7 +377,8 @@ class DeviceRun:
         """Average duration of the dominant (solve) kernel alone, CUDA events on the launching stream."""
         torch = self.torch
         tot = 0.0
-        for i in range(reps):
+        for rep in range(reps):
+            i = rep % len(self.xs)                     # --steps / --warmup may be smaller than reps
             self.xs[i].copy_(self.x0)
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

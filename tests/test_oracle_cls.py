@@ -112,3 +112,33 @@ def test_cls_batch_equals_single(oracle):
         x, f, ib, st = oracle.cls_solve("misc_2fcn", x0[:, b], lower=[0.0, 0.0], upper=[6.0, 6.0])
         assert np.array_equal(x, xb[:, b]) and np.array_equal(f, fb[:, b]) and st == stb[b]
         assert ib["iter_count"] == ibb["iter_count"][b] and ib["fcn_count"] == ibb["fcn_count"][b]
+
+
+def test_cls_matches_scipy_bounded_least_squares_when_limits_are_inactive(oracle):
+    """Independent cross-check (not an oracle): scipy's trust-region-reflective bounded least squares reaches the
+    same minimiser on the noisy cubic fits when the limits do not bind.  With binding limits the reference's
+    method only promises feasibility and descent (that is all its own bounds test asserts), which is checked too."""
+    from scipy.optimize import least_squares
+
+    from nonlin_b200 import workloads as W
+
+    B = 24
+    w = W.c1_lm_polyfit(B)
+    xp = W.POLYFIT_XP
+
+    def res(c, y):
+        return c[0] * xp ** 3 + c[1] * xp ** 2 + c[2] * xp + c[3] - y
+
+    x0 = np.full((4, B), 0.5)
+    lo, hi = [-10.0] * 4, [10.0] * 4
+    x, f, ib, st = oracle.cls_solve_batch("lsq_poly_fit", x0, sys=w["args"], lower=lo, upper=hi)
+    assert np.all(st == 0)
+    for b in range(B):
+        r = least_squares(res, x0[:, b], bounds=(lo, hi), args=(w["args"][:, b],), xtol=1e-14, ftol=1e-14, gtol=1e-14)
+        assert np.abs(x[:, b] - r.x).max() < 1e-5
+        assert 0.5 * np.sum(f[:, b] ** 2) <= r.cost * (1 + 1e-10)
+    lo, hi = np.array([0.0, -1.0, 0.0, 0.0]), np.array([1.0, 1.0, 2.0, 2.0])      # x1 <= 1 cuts off the optimum
+    x, f, ib, st = oracle.cls_solve_batch("lsq_poly_fit", x0, sys=w["args"], lower=lo, upper=hi)
+    f0 = np.stack([res(x0[:, b], w["args"][:, b]) for b in range(B)], axis=1)
+    assert np.all(x >= lo[:, None]) and np.all(x <= hi[:, None])
+    assert np.all(np.sum(f ** 2, axis=0) <= np.sum(f0 ** 2, axis=0))

@@ -136,6 +136,23 @@ void nlo_lmfactor(int m, int n, double* a, int* ipvt, double* rdiag, double* acn
     lm_factor(m, n, R(a), true, ipvt, R(rdiag), R(acnorm), wa.data());
 }
 
+// DGELS restatement on a caller's m x n matrix (column-major) and right-hand side; returns LAPACK info
+int nlo_dgels(int m, int n, double* a, double* b) {
+    std::vector<real> tau(n), work(n);
+    return la_dgels(m, n, R(a), m, R(b), tau.data(), work.data());
+}
+// qr_factor(a, tau=, qr=) + solve_qr(qr, tau, b) as the constrained solver uses them: x(1:n) in b
+void nlo_qr_solve(int m, int n, double* a, double* b) {
+    std::vector<real> tau(n), work(n);
+    la_dgeqr2(m, n, R(a), m, tau.data(), work.data());
+    la_dorm2r_lt_vec(m, n, R(a), m, tau.data(), R(b));
+    la_dtrsv_unn(n, R(a), m, R(b));
+}
+void nlo_dgemv(int trans, int m, int n, const double* a, const double* x, double* y) {
+    if (trans) la_dgemv_t(m, n, real(1.0), R(a), m, R(x), R(y));
+    else la_dgemv_n(m, n, real(1.0), R(a), m, R(x), R(y));
+}
+
 // one system, contiguous x(n), fvec(m), sys(sys_len)
 int nlo_solve(int solver, int fcn_id, int m, int n, const Params* prm, double* x, double* fvec, const double* sys,
               const double* shared, IterBehavior* ib) {

@@ -82,3 +82,57 @@ def test_lm_solution_agrees_with_minpack(oracle):
         res = lambda p: p[0] * np.exp(-p[1] * t) + p[2] * np.exp(-p[3] * t) - y
         ref, _ = sopt.leastsq(res, w["x0"][:, b], xtol=1e-12, ftol=1e-12)
         assert abs(np.linalg.norm(res(x[:, b])) - np.linalg.norm(res(ref))) <= 1e-8
+
+
+# ---- pieces behind constrained_least_squares_solver and polynomial%fit ---------------------------
+def _f(a):
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+@pytest.mark.parametrize("m,n", [(2, 2), (21, 4), (64, 8), (300, 7)])
+def test_unpivoted_qr_solve_matches_lapack(oracle, m, n):
+    """qr_factor(a, tau=, qr=) + solve_qr(qr, tau, b) restated as DGEQR2 + DORM2R('L','T') + DTRSV against LAPACK's
+    DGEQRF + DORMQR + DTRTRS (blocked, possibly FMA: agreement to rounding, not bits)."""
+    from scipy.linalg import lapack
+
+    rng = np.random.default_rng(10 * m + n)
+    a = _f(rng.standard_normal((m, n)))
+    b = rng.standard_normal(m)
+    qr, tau, _, info = lapack.dgeqrf(a)
+    cq, _, info2 = lapack.dormqr("L", "T", qr, tau, b.reshape(-1, 1).copy(order="F"), max(1, 64 * n))
+    xs, info3 = lapack.dtrtrs(qr[:n, :n], cq[:n], lower=0)
+    assert info == 0 and info2 == 0 and info3 == 0
+    a2, b2 = a.copy(order="F"), b.copy()
+    oracle.lib.nlo_qr_solve(m, n, a2.ctypes.data_as(C.c_void_p), b2.ctypes.data_as(C.c_void_p))
+    assert np.allclose(np.triu(a2[:n]), np.triu(qr[:n]), rtol=1e-12, atol=1e-13)      # same R, same signs
+    assert np.allclose(b2[:n], xs[:, 0], rtol=1e-10, atol=1e-12)
+    assert np.allclose(b2[:n], np.linalg.lstsq(a, b, rcond=None)[0], rtol=1e-9, atol=1e-11)
+
+
+@pytest.mark.parametrize("m,n", [(21, 4), (100, 6), (9, 8)])
+@pytest.mark.parametrize("scale_a,scale_b", [(1.0, 1.0), (2.0 ** -990, 1.0), (2.0 ** 985, 1.0), (1.0, 2.0 ** 990), (1.0, 2.0 ** -1000)])
+def test_dgels_matches_lapack_including_scaling_branches(oracle, m, n, scale_a, scale_b):
+    from scipy.linalg import lapack
+
+    rng = np.random.default_rng(m + 100 * n)
+    t = np.linspace(0.2, 1.5, m)
+    a = _f(np.vander(t, n, increasing=True) * scale_a)
+    b = rng.standard_normal(m) * scale_b
+    lqr, x, info = lapack.dgels(a, b)
+    assert info == 0
+    a2, b2 = a.copy(order="F"), b.copy()
+    assert oracle.lib.nlo_dgels(m, n, a2.ctypes.data_as(C.c_void_p), b2.ctypes.data_as(C.c_void_p)) == 0
+    ref = x[:n]
+    assert np.allclose(b2[:n], ref, rtol=1e-7, atol=1e-9 * np.abs(ref).max())
+
+
+def test_dgemv_forms(oracle):
+    rng = np.random.default_rng(3)
+    a = _f(rng.standard_normal((21, 4)))
+    x4, x21 = rng.standard_normal(4), rng.standard_normal(21)
+    y = np.zeros(21)
+    oracle.lib.nlo_dgemv(0, 21, 4, a.ctypes.data_as(C.c_void_p), x4.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p))
+    assert np.allclose(y, a @ x4, rtol=1e-14, atol=1e-14)
+    yt = np.zeros(4)
+    oracle.lib.nlo_dgemv(1, 21, 4, a.ctypes.data_as(C.c_void_p), x21.ctypes.data_as(C.c_void_p), yt.ctypes.data_as(C.c_void_p))
+    assert np.allclose(yt, a.T @ x21, rtol=1e-14, atol=1e-14)

@@ -38,6 +38,8 @@ struct nlb_handle {
     int num_sms = 0;
     void* dwork = nullptr;                         // grow-only workspace of the polynomial-fit kernel
     size_t dwork_cap = 0;
+    cudaEvent_t ev_work = nullptr;                 // last kernel that used dwork (orders users on different streams)
+    bool work_used = false;
     cudaStream_t pipe[2] = {nullptr, nullptr};   // copy/compute pipeline for host-resident batches
     cudaEvent_t ev_in = nullptr, ev_out[2] = {nullptr, nullptr};
     std::mutex mu;
@@ -694,6 +696,7 @@ int nlb_create(nlb_handle** handle, int device) {
         cudaEventCreateWithFlags(&h->ev_out[1], cudaEventDisableTiming) != cudaSuccess ||
         cudaMalloc(&h->dstats, sizeof(int64_t) * NLB_STAT_COUNT) != cudaSuccess ||
         cudaMalloc(&h->dcursor, sizeof(unsigned long long) * 16) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_work, cudaEventDisableTiming) != cudaSuccess ||
         cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
         delete h;
         return NLB_ERR_CUDA;
@@ -716,6 +719,7 @@ int nlb_destroy(nlb_handle* h) {
         if (h->ev_out[q]) cudaEventDestroy(h->ev_out[q]);
     }
     if (h->ev_in) cudaEventDestroy(h->ev_in);
+    if (h->ev_work) cudaEventDestroy(h->ev_work);
     delete h;
     return NLB_OK;
 }
@@ -882,6 +886,8 @@ int nlb_polynomial_fit_batch(nlb_handle* h, int64_t B, int npts, int order, int 
             h->dwork_cap = (size_t)T * per_thread;
         }
         const unsigned grid = (unsigned)(T / 128);
+        // the workspace is shared by every call on this handle: a fit launched on another stream waits for the last one
+        if (h->work_used) NLB_CUDA(h, cudaStreamWaitEvent(s, h->ev_work, 0));
         switch (nc) {
 #define X(NC)                                                                                                       \
     case NC:                                                                                                        \
@@ -892,6 +898,8 @@ int nlb_polynomial_fit_batch(nlb_handle* h, int64_t B, int npts, int order, int 
             X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
 #undef X
         }
+        NLB_CUDA(h, cudaEventRecord(h->ev_work, s));
+        h->work_used = true;
     }
     ++h->launches;
     NLB_CUDA(h, cudaGetLastError());

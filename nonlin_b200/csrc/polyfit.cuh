@@ -12,7 +12,7 @@
 // Mapping.  The m x n Vandermonde matrix and the right-hand side (n + 1 columns of m rows) of one data set live in
 // a workspace laid out [column][row][thread]: lane-contiguous, so every pass of the factorisation is conflict-free
 // in shared memory and fully coalesced in global memory.  Small fits (128 threads' workspaces fit one CTA's shared
-// memory: m (n + 1) <= 220 doubles) run out of shared memory; larger ones use a global workspace with the grid
+// memory: m (n + 1) <= 225 doubles) run out of shared memory; larger ones use a global workspace with the grid
 // capped (persistent, grid-stride over data sets) so that the live workspace stays inside the 126 MB L2.  H(i) is applied to y in the same two passes that apply it to the trailing
 // columns of A (LAPACK does it afterwards; v_i is final by then either way, so the arithmetic is identical), each
 // column's dot product accumulating in row order.  Algorithmic HBM bytes per data set: 8 (m + m + n) (+ 4 status)

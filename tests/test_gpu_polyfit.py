@@ -154,3 +154,19 @@ def test_full_size_properties(engine, oracle):
     xs = np.ones((4, 4096))
     nb.least_squares_solver().solve(obj, xs, args=np.ascontiguousarray(y[:, :4096]))
     assert np.abs(xs[::-1] - c[:, :4096]).max() < 1e-4
+
+
+@pytest.mark.parametrize("npts", [44, 45, 46])
+def test_storage_variant_boundary(engine, oracle, npts):
+    """npts (order + 2) = 225 is the last fit that runs from shared memory (225 KB per CTA); one more point switches to
+    the global workspace.  Both sides of the boundary must give the oracle's bits."""
+    import nonlin_b200 as nb
+
+    rng = np.random.default_rng(npts)
+    B = 700
+    x = rng.uniform(-1.0, 1.5, size=(npts, B))
+    y = rng.standard_normal((npts, B))
+    p = nb.polynomial()
+    st = p.fit(x, y, 4)
+    co, sto = oracle.polyfit_batch(x, y, 4)
+    assert np.array_equal(st, sto) and np.array_equal(p.get_all(), co)

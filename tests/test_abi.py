@@ -184,3 +184,15 @@ def test_fortran_binding_declares_every_solver_entry_point():
     block = src[src.index("type, bind(C) :: nlb_params"):src.index("end type")]
     pos = [block.index(f) for f in fields]
     assert pos == sorted(pos)
+
+
+def test_header_is_valid_c99_and_cxx():
+    """The boundary is a C ABI: include/nonlin_batch.h must compile as plain C as well as C++."""
+    import shutil
+    import subprocess
+
+    hdr = os.path.join(ROOT, "include", "nonlin_batch.h")
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    subprocess.check_call([cxx, "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr])

@@ -140,8 +140,28 @@ def oracle_solve_batch(o, w, x0, sysd, **kw):
     return o.solve_batch(w["solver"], w["fcn"], x0, m=w["m"], sys=sysd, shared=w["shared"], **kw)
 
 
-def cpu_port_throughput(w, min_seconds=4.0, max_reps=50, sample=None):
-    """Time the CPU oracle (OpenMP, all host cores) on the workload's batch (or a slice of it)."""
+def parity_report(engine_out, oracle_out):
+    """Engine results against the CPU port's on the same systems (the port as the checker): the north_star bar is
+    x and f within 1e-10 relative on converged systems and equal iteration / evaluation / Jacobian counts on >= 99 %."""
+    x, f, ib, st = engine_out
+    xo, fo, ibo, sto = oracle_out
+    n = st.shape[0]
+    ibo = ibo.view(np.int32).reshape(n, 7)
+    ok = sto == 0
+    sx = np.maximum(np.abs(xo).max(axis=0), 1e-300)
+    sf = np.maximum(np.abs(fo).max(axis=0), 1e-300)
+    close = (np.abs(x - xo).max(axis=0) <= 1e-10 * sx) & (np.abs(f - fo).max(axis=0) <= 1e-10 * sf + 1e-300)
+    bit = (x == xo).all(axis=0) & (f == fo).all(axis=0)
+    counts = (ib[:, :3] == ibo[:, :3]).all(axis=1)
+    return {"systems_checked": int(n), "status_equal": float((st == sto).mean()),
+            "x_f_within_1e-10_on_converged": float(close[ok].mean()) if ok.any() else None,
+            "x_f_bit_identical": float(bit.mean()), "iter_nfev_njac_equal": float(counts.mean()),
+            "flags_equal": float((ib[:, 4:] == ibo[:, 4:]).all(axis=1).mean())}
+
+
+def cpu_port_throughput(w, min_seconds=4.0, max_reps=50, sample=None, engine_out=None):
+    """Time the CPU oracle (OpenMP, all host cores) on the workload's batch (or a slice of it).  With engine_out =
+    (x, f, ib[B,7], status) of the engine on the same batch, the port's results also serve as the parity check."""
     from oracle.nl_oracle import Oracle
 
     o = Oracle()
@@ -156,12 +176,19 @@ def cpu_port_throughput(w, min_seconds=4.0, max_reps=50, sample=None):
     reps, elapsed, conv = 0, 0.0, 0
     while (elapsed < min_seconds and reps < max_reps) or reps < 2:
         t0 = time.perf_counter()
-        _, _, _, st = oracle_solve_batch(o, w, x0, sysd, params=p, nthreads=cores)
+        xo, fo, ibo, st = oracle_solve_batch(o, w, x0, sysd, params=p, nthreads=cores)
         elapsed += time.perf_counter() - t0
         conv += int((st == 0).sum())
         reps += 1
-    return {"value": conv / elapsed, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d systems of the batch x %d passes, OpenMP schedule(dynamic), one system per thread at a time" % (nsub, reps)}
+    out = {"value": conv / elapsed, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": "%d systems of the batch x %d passes, OpenMP schedule(dynamic), one system per thread at a time" % (nsub, reps)}
+    if engine_out is not None:
+        try:
+            out["parity"] = parity_report(tuple(a[..., :nsub] if a.ndim == 2 and a.shape[1] != 7 else a[:nsub] for a in engine_out),
+                                          (xo, fo, ibo, st))
+        except Exception as ex:      # the parity report must never hide the measurement
+            out["parity"] = {"error": repr(ex)}
+    return out
 
 
 def flops_per_system(w, sample=4096):
@@ -513,7 +540,10 @@ def run_engine(args):
         "hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                 "bytes_per_system": w["bytes_per_system"], "peak_source": hbm_src},
     }
-    cpu = cpu_port_throughput(w) if world == 1 else None
+    # results of the first step of the batch (every step solves the same systems), for the parity report
+    eng_out = (run.xs[0].cpu().numpy(), run.f[0].cpu().numpy(), run.ib[0].cpu().numpy().reshape(-1, 7),
+               run.status[0].cpu().numpy()) if world == 1 else None
+    cpu = cpu_port_throughput(w, engine_out=eng_out) if world == 1 else None
 
     extras = {}
     if not args.no_extras and world == 1:

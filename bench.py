@@ -159,6 +159,20 @@ def parity_report(engine_out, oracle_out):
             "flags_equal": float((ib[:, 4:] == ibo[:, 4:]).all(axis=1).mean())}
 
 
+def extra_parity(w, run, max_systems):
+    """Parity of a DeviceRun's first-step results against the CPU port on the first max_systems systems."""
+    from oracle.nl_oracle import Oracle
+
+    o = Oracle()
+    n = min(w["x0"].shape[1], max_systems)
+    x0 = np.ascontiguousarray(w["x0"][:, :n])
+    sysd = None if w["args"] is None else np.ascontiguousarray(w["args"][:, :n])
+    ref = oracle_solve_batch(o, w, x0, sysd, params=oracle_params(o, w))
+    eng = (run.xs[0][:, :n].cpu().numpy(), run.f[0][:, :n].cpu().numpy(), run.ib[0][:n].cpu().numpy().reshape(-1, 7),
+           run.status[0][:n].cpu().numpy())
+    return parity_report(eng, ref)
+
+
 def cpu_port_throughput(w, min_seconds=4.0, max_reps=50, sample=None, engine_out=None):
     """Time the CPU oracle (OpenMP, all host cores) on the workload's batch (or a slice of it).  With engine_out =
     (x, f, ib[B,7], status) of the engine on the same batch, the port's results also serve as the parity check."""
@@ -560,6 +574,10 @@ def run_engine(args):
                 extras[name] = {"workload": workload_label(we, default_batch(name)), "value": c * 5 / (sm * 1e-3), "unit": UNIT,
                                 "ms_per_step": sm / 5, "fp64_tflops": fle * default_batch(name) / (km / 5 * 1e-3) / 1e12,
                                 "flops_per_system": fle}
+                try:                      # engine vs CPU port on (a slice of) the same batch
+                    extras[name]["parity"] = extra_parity(we, r, 1 << 18)
+                except Exception as ex:
+                    extras[name]["parity"] = {"error": repr(ex)}
                 del r
             except Exception as ex:   # an extra must never hide the headline
                 extras[name] = {"error": repr(ex)}

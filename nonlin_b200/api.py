@@ -148,7 +148,34 @@ def _device_of(*arrays):
     torch = sys.modules.get("torch")
     if torch is not None and torch.cuda.is_available() and torch.cuda.is_initialized():
         return torch.cuda.current_device()
+    # one process per GPU (torchrun): host-array calls go to this rank's GPU, not to device 0
+    import os
+
+    lr = os.environ.get("LOCAL_RANK")
+    if lr is not None and lr.isdigit():
+        return int(lr)
     return None
+
+
+def _check_i32(name, a, B, width=None):
+    """`status` (int32, (B,)) and `ib` (IB_DTYPE (B,) or int32 (B, 7)) are written by the engine in full: a short or
+    narrow array would be overrun silently, so refuse it (NLB_ERR_SIZE / TypeError) before the call."""
+    if a is None:
+        return
+    if _is_torch(a):
+        import torch
+
+        ok = a.dtype == torch.int32
+        shape_ok = tuple(a.shape) == ((B,) if width is None else (B, width))
+    elif width is not None and a.dtype == IB_DTYPE:
+        ok, shape_ok = True, tuple(a.shape) == (B,)
+    else:
+        ok = a.dtype == np.int32
+        shape_ok = tuple(a.shape) == ((B,) if width is None else (B, width))
+    if not ok:
+        raise TypeError("%s must be int32%s" % (name, " (or the iteration_behavior record dtype)" if width else ""))
+    if not shape_ok:
+        raise NonlinError(_lib.NLB_ERR_SIZE, "%s has shape %s for a batch of %d" % (name, tuple(a.shape), B))
 
 
 def _check_f64(name, a, shape):
@@ -396,6 +423,8 @@ class equation_solver:
                 status = torch.zeros(B, dtype=torch.int32, device=x.device)
             else:
                 status = np.zeros(B, dtype=np.int32)
+        _check_i32("status", status, B)
+        _check_i32("ib", ib, B, 7)
         eng = self._engine or default_engine(_device_of(x, fvec, args, ib, status) or 0)
         p = self._params(fcn)
         entry = getattr(_LIB, self._entry)
@@ -690,6 +719,8 @@ class equation_solver_1var:
         if status is None:
             status = _empty_like(x, (B,), dtype="int32")
             status[...] = 0
+        _check_i32("status", status, B)
+        _check_i32("ib", ib, B, 7)
         eng = self._engine or default_engine(_device_of(x, f, args, ib, status) or 0)
         p = _lib.nlb_params_1var()
         _LIB.nlb_params_1var_default(C.byref(p))
@@ -759,6 +790,7 @@ class polynomial:
         c = _empty_like(y, (int(order) + 1, B))
         if status is None:
             status = _empty_like(y, (B,), dtype="int32")
+        _check_i32("status", status, B)
         eng = self._engine or default_engine(_device_of(x, y) or 0)
         eng.check(_LIB.nlb_polynomial_fit_batch(eng._h, B, npts, int(order), int(thru_zero), int(shared), _ptr(x), _ptr(y),
                                                 _ptr(c), _ptr(status),

@@ -1,6 +1,7 @@
 // coop_kernels.cu — launchers of the CTA-per-system kernels (run-time sized residual families).
 #include "coop_kernels.cuh"
 
+#include "launch_cfg.cuh"
 #include "coop_broyden.cuh"
 #include "coop_lm.cuh"
 #include "coop_lm_cta.cuh"
@@ -16,13 +17,8 @@ template <class F, int N>
 int launch_broyden(const DevParams& p, long long nsys, long long B, double* x, double* fvec, const double* sys, const double* shared,
                    nlb_iteration_behavior* ib, int32_t* status, cudaStream_t s, int64_t* launches) {
     using S = CoopBroydenSmem<N>;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(coop_broyden_kernel<F, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES) !=
-            cudaSuccess)
-            return NLB_ERR_CUDA;
-        configured = true;
-    }
+    KernelCfg cfg;
+    if (kernel_cfg<coop_broyden_kernel<F, N>>(N, S::BYTES, &cfg) != cudaSuccess) return NLB_ERR_CUDA;
     coop_broyden_kernel<F, N><<<(unsigned)nsys, N, S::BYTES, s>>>(p, nsys, B, x, fvec, sys, shared, ib, status);
     ++*launches;
     return cudaGetLastError() == cudaSuccess ? NLB_OK : NLB_ERR_CUDA;
@@ -101,32 +97,14 @@ template <class F, int N>
 int launch_lm(const DevParams& p, long long ntot, long long B, int m, double* x, double* fvec, const double* sys, const double* shared,
               nlb_iteration_behavior* ib, int32_t* status, cudaStream_t s, int64_t* launches) {
     using S = CoopLmSmem<N>;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(coop_lm_kernel<F, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES) != cudaSuccess)
-            return NLB_ERR_CUDA;
-        configured = true;
-    }
-    // HBM workspace: (n + 3) * m doubles per resident lane, allocated stream-ordered and capped at 8 GiB
-    // per launch; larger batches run as consecutive launches over contiguous system ranges.
+    KernelCfg cfg;
+    if (kernel_cfg<coop_lm_kernel<F, N>>(32 * N, S::BYTES, &cfg) != cudaSuccess) return NLB_ERR_CUDA;
+    // HBM workspace: (n + 3) * m doubles per resident lane, allocated stream-ordered.  Persistent CTAs: only as
+    // many as are resident at once; their 32 lanes pull systems from a cursor, so the workspace is sized by the
+    // resident lanes (148 SMs x CTAs per SM x 32), not by the batch.
     const size_t per_sys = (size_t)(N + 3) * (size_t)m * sizeof(double);
-    long long chunk = (long long)((8ull << 30) / per_sys) / 32 * 32;
-    if (chunk < 32) chunk = 32;
-    if (chunk > ntot) chunk = (ntot + 31) / 32 * 32;
-    // Persistent CTAs: only as many as are resident at once; their 32 lanes pull systems from a cursor,
-    // so the HBM workspace is sized by the resident lanes, not by the batch.
-    static int ctas_per_sm = 0, num_sms = 0;
-    if (ctas_per_sm == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, coop_lm_kernel<F, N>, 32 * N, S::BYTES) != cudaSuccess)
-            return NLB_ERR_CUDA;
-        if (ctas_per_sm < 1) ctas_per_sm = 1;
-    }
     long long grid = (ntot + 31) / 32;
-    if (grid > (long long)num_sms * ctas_per_sm) grid = (long long)num_sms * ctas_per_sm;
-    (void)chunk;
+    if (grid > (long long)cfg.num_sms * cfg.ctas_per_sm) grid = (long long)cfg.num_sms * cfg.ctas_per_sm;
     double* ws = nullptr;
     if (cudaMallocAsync((void**)&ws, per_sys * 32 * (size_t)grid + 64, s) != cudaSuccess) return NLB_ERR_CUDA;
     unsigned long long* cursor = reinterpret_cast<unsigned long long*>(ws + (size_t)(N + 3) * m * 32 * (size_t)grid);
@@ -143,18 +121,10 @@ template <class F, int N>
 int launch_wlm(const DevParams& p, long long ntot, long long B, int m, double* x, double* fvec, const double* sys,
                const double* shared, nlb_iteration_behavior* ib, int32_t* status, cudaStream_t s, int64_t* launches) {
     using S = WlmSmem<N>;
-    static int ctas_per_sm = 0, num_sms = 0;
-    if (ctas_per_sm == 0) {
-        int dev = 0;
-        if (cudaFuncSetAttribute(wlm_kernel<F, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES) != cudaSuccess ||
-            cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, wlm_kernel<F, N>, 32 * N, S::BYTES) != cudaSuccess)
-            return NLB_ERR_CUDA;
-        if (ctas_per_sm < 1) ctas_per_sm = 1;
-    }
+    KernelCfg cfg;
+    if (kernel_cfg<wlm_kernel<F, N>>(32 * N, S::BYTES, &cfg) != cudaSuccess) return NLB_ERR_CUDA;
     long long grid = ntot;
-    if (grid > (long long)num_sms * ctas_per_sm) grid = (long long)num_sms * ctas_per_sm;
+    if (grid > (long long)cfg.num_sms * cfg.ctas_per_sm) grid = (long long)cfg.num_sms * cfg.ctas_per_sm;
     const size_t per_cta = (size_t)(N + 3) * (size_t)m;          // doubles
     double* ws = nullptr;
     if (cudaMallocAsync((void**)&ws, (per_cta * (size_t)grid + 8) * sizeof(double), s) != cudaSuccess) return NLB_ERR_CUDA;

@@ -12,6 +12,7 @@
 #include <cstdlib>
 
 #include "coop_kernels.cuh"
+#include "launch_cfg.cuh"
 #include "polyfit.cuh"
 #include "scalar_solvers.cuh"
 #include "tps_cls.cuh"
@@ -33,8 +34,6 @@ struct nlb_handle {
     void* dbuf[NSLOT] = {nullptr};
     size_t dcap[NSLOT] = {0};
     int64_t* dstats = nullptr;
-    unsigned long long* dcursor = nullptr;         // work-queue cursors of the persistent kernels (16 slots)
-    unsigned cursor_next = 0;
     int num_sms = 0;
     void* dwork = nullptr;                         // grow-only workspace of the polynomial-fit kernel
     size_t dwork_cap = 0;
@@ -59,6 +58,12 @@ int set_err(nlb_handle* h, int code, const char* what, cudaError_t ce = cudaSucc
     }
     return code;
 }
+
+// Make the handle's device current for the rest of the scope; the caller's device is restored on return.
+#define NLB_DEVICE(h)                                                                        \
+    DeviceGuard nlb_device_guard((h)->device);                                               \
+    if (nlb_device_guard.err != cudaSuccess)                                                 \
+        return set_err((h), NLB_ERR_NO_DEVICE, "cudaSetDevice", nlb_device_guard.err)
 
 #define NLB_CUDA(h, call)                                                   \
     do {                                                                    \
@@ -375,24 +380,32 @@ int launch_tps_solve(nlb_handle* h, const DevParams& p, long long nsys, long lon
     return NLB_OK;
 }
 
+// Work-queue cursor of a persistent kernel: allocated stream-ordered with the launch, zeroed, and released after the
+// kernel on the same stream, so launches in flight on different streams never share one.
+int cursor_acquire(nlb_handle* h, cudaStream_t s, unsigned long long** cursor) {
+    NLB_CUDA(h, cudaMallocAsync((void**)cursor, sizeof(unsigned long long), s));
+    NLB_CUDA(h, cudaMemsetAsync(*cursor, 0, sizeof(unsigned long long), s));
+    return NLB_OK;
+}
+
 template <class F>
 int launch_tps_newton_refill(nlb_handle* h, const DevParams& p, long long nsys, long long B, double* x, double* fvec,
                              const double* sys, const double* shared, nlb_iteration_behavior* ib, int32_t* status,
                              cudaStream_t s) {
     if (nsys == 0) return NLB_OK;
-    static int ctas_per_sm = 0;
-    if (ctas_per_sm == 0) {
-        NLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, tps_newton_refill_kernel<F>, TPS_BLOCK, 0));
-        if (ctas_per_sm < 1) ctas_per_sm = 1;
-    }
+    KernelCfg cfg;
+    NLB_CUDA(h, kernel_cfg<tps_newton_refill_kernel<F>>(TPS_BLOCK, 0, &cfg));
     long long grid = (nsys + TPS_BLOCK - 1) / TPS_BLOCK;
-    const long long resident = (long long)h->num_sms * ctas_per_sm;
+    const long long resident = (long long)cfg.num_sms * cfg.ctas_per_sm;
     if (grid > resident) grid = resident;
-    unsigned long long* cursor = h->dcursor + (h->cursor_next++ & 15u);
-    NLB_CUDA(h, cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), s));
+    unsigned long long* cursor = nullptr;
+    int rc = cursor_acquire(h, s, &cursor);
+    if (rc) return rc;
     tps_newton_refill_kernel<F><<<(unsigned)grid, TPS_BLOCK, 0, s>>>(p, nsys, B, cursor, x, fvec, sys, shared, ib, status);
     ++h->launches;
-    NLB_CUDA(h, cudaGetLastError());
+    const cudaError_t le = cudaGetLastError();
+    NLB_CUDA(h, cudaFreeAsync(cursor, s));
+    NLB_CUDA(h, le);
     return NLB_OK;
 }
 
@@ -403,16 +416,12 @@ int launch_tps_lm_smem(nlb_handle* h, const DevParams& p, long long nsys, long l
     // Measured on B200 (C1, 2^20 fits): 8.85 ms with the Jacobian in shared memory (256 threads per SM) against
     // 6.98 ms with it in local memory (384 threads per SM) - the kernel is latency-bound and occupancy wins.  The
     // shared-memory variant stays selectable for re-measurement (NLB_LM_SMEM=1); it is bit-identical.
-    static int use_smem = -1;
-    if (use_smem < 0) use_smem = std::getenv("NLB_LM_SMEM") ? 1 : 0;
+    static const int use_smem = std::getenv("NLB_LM_SMEM") ? 1 : 0;      // magic static: thread-safe
     if (!use_smem) return launch_tps_solve<F, SOLVER_LM>(h, p, nsys, B, x, fvec, sys, shared, ib, status, s);
     if (nsys == 0) return NLB_OK;
     constexpr size_t smem = sizeof(double) * F::M * F::N * TPS_BLOCK;
-    static bool configured = false;
-    if (!configured) {
-        NLB_CUDA(h, cudaFuncSetAttribute(tps_lm_smem_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    KernelCfg cfg;
+    NLB_CUDA(h, kernel_cfg<tps_lm_smem_kernel<F>>(TPS_BLOCK, smem, &cfg));
     const unsigned grid = (unsigned)((nsys + TPS_BLOCK - 1) / TPS_BLOCK);
     tps_lm_smem_kernel<F><<<grid, TPS_BLOCK, smem, s>>>(p, nsys, B, x, fvec, sys, shared, ib, status);
     ++h->launches;
@@ -449,19 +458,19 @@ int dispatch_tps(nlb_handle* h, int fcn_id, const DevParams& p, long long nsys, 
 template <class F>
 int launch_cls(nlb_handle* h, const DevParams& p, const DevCls& o, long long nsys, long long B, double* x, double* fvec,
                const double* sys, const double* shared, nlb_iteration_behavior* ib, int32_t* status, cudaStream_t s) {
-    static int ctas_per_sm = 0;
-    if (ctas_per_sm == 0) {
-        NLB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, tps_cls_kernel<F>, TPS_BLOCK, 0));
-        if (ctas_per_sm < 1) ctas_per_sm = 1;
-    }
+    KernelCfg cfg;
+    NLB_CUDA(h, kernel_cfg<tps_cls_kernel<F>>(TPS_BLOCK, 0, &cfg));
     long long grid = (nsys + TPS_BLOCK - 1) / TPS_BLOCK;
-    const long long resident = (long long)h->num_sms * ctas_per_sm;
+    const long long resident = (long long)cfg.num_sms * cfg.ctas_per_sm;
     if (grid > resident) grid = resident;
-    unsigned long long* cursor = h->dcursor + (h->cursor_next++ & 15u);
-    NLB_CUDA(h, cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), s));
+    unsigned long long* cursor = nullptr;
+    int rc = cursor_acquire(h, s, &cursor);
+    if (rc) return rc;
     tps_cls_kernel<F><<<(unsigned)grid, TPS_BLOCK, 0, s>>>(p, o, nsys, B, cursor, x, fvec, sys, shared, ib, status);
     ++h->launches;
-    NLB_CUDA(h, cudaGetLastError());
+    const cudaError_t le = cudaGetLastError();
+    NLB_CUDA(h, cudaFreeAsync(cursor, s));
+    NLB_CUDA(h, le);
     return NLB_OK;
 }
 
@@ -478,8 +487,6 @@ int dispatch_cls(nlb_handle* h, int fcn_id, const DevParams& p, const DevCls& o,
     }
 }
 
-int ensure_device(nlb_handle* h);
-
 #define NLB_FCN1_LIST(X) X(SinxDivX) X(SinxDivXA) X(CubicWallis) X(ExpMinusX) X(CubicArgs)
 
 int solve_1var_batch(nlb_handle* h, int solver, const nlb_params_1var* params, int fcn_id, int64_t B,
@@ -492,8 +499,8 @@ int solve_1var_batch(nlb_handle* h, int solver, const nlb_params_1var* params, i
     if (fcn_id < 0 || fcn_id >= FCN1_COUNT) return set_err(h, NLB_ERR_UNKNOWN_FCN, "unknown one-variable function id");
     const Fcn1Info& fi = fcn1_table()[fcn_id];
     if (fi.args_len > 0 && B > 0 && !args) return set_err(h, NLB_ERR_INVALID_ARGUMENT, "this function needs per-equation args");
-    int rc = ensure_device(h);
-    if (rc) return rc;
+    NLB_DEVICE(h);
+    int rc = NLB_OK;
     if (B == 0) return NLB_OK;
     cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
     Staged a1, a2, ax, af, aa, aib, ast;
@@ -552,13 +559,6 @@ int check_sizes(nlb_handle* h, int fcn_id, int* m, int* n, int* sys_len, int* sh
     return NLB_OK;
 }
 
-int ensure_device(nlb_handle* h) {
-    if (!h) return NLB_ERR_INVALID_ARGUMENT;
-    cudaError_t e = cudaSetDevice(h->device);
-    if (e != cudaSuccess) return set_err(h, NLB_ERR_NO_DEVICE, "cudaSetDevice", e);
-    return NLB_OK;
-}
-
 int solve_batch(nlb_handle* h, int solver, const nlb_params* params, int fcn_id, int64_t B, int m, int n, double* x,
                 double* fvec, const double* sys, const double* shared, nlb_iteration_behavior* ib, int32_t* status,
                 void* stream, const DevCls* cls = nullptr) {
@@ -573,8 +573,7 @@ int solve_batch(nlb_handle* h, int solver, const nlb_params* params, int fcn_id,
     if (!lsq && n != m) return set_err(h, NLB_ERR_SIZE, "Newton / quasi-Newton need m == n");
     if (sys_len > 0 && B > 0 && !sys) return set_err(h, NLB_ERR_INVALID_ARGUMENT, "this residual needs per-system data");
     if (shared_len > 0 && B > 0 && !shared) return set_err(h, NLB_ERR_INVALID_ARGUMENT, "this residual needs shared data");
-    rc = ensure_device(h);
-    if (rc) return rc;
+    NLB_DEVICE(h);
     if (B == 0) return NLB_OK;
     cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
 
@@ -634,11 +633,10 @@ int solve_batch(nlb_handle* h, int solver, const nlb_params* params, int fcn_id,
     // 4 chunks 1.58 ms, 8 chunks 1.68 ms, 16 chunks 1.83 ms, 32 chunks 2.14 ms - per-copy overhead outweighs the
     // shorter pipeline fill beyond 4.
     int nchunk = B >= (1 << 18) ? 4 : (B >= (1 << 15) ? 2 : 1);
-    static int chunk_override = -1;
-    if (chunk_override < 0) {
+    static const int chunk_override = [] {
         const char* e = std::getenv("NLB_HOST_CHUNKS");      // tuning knob
-        chunk_override = e ? std::atoi(e) : 0;
-    }
+        return e ? std::atoi(e) : 0;
+    }();
     if (chunk_override > 0) nchunk = chunk_override;
     const long long chunk = (B + nchunk - 1) / nchunk;
     NLB_CUDA(h, cudaEventRecord(h->ev_in, s));
@@ -685,7 +683,8 @@ int nlb_create(nlb_handle** handle, int device) {
         cudaGetLastError();
         return NLB_ERR_NO_DEVICE;
     }
-    if (cudaSetDevice(device) != cudaSuccess) return NLB_ERR_NO_DEVICE;
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return NLB_ERR_NO_DEVICE;
     nlb_handle* h = new nlb_handle();
     h->device = device;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -695,7 +694,6 @@ int nlb_create(nlb_handle** handle, int device) {
         cudaEventCreateWithFlags(&h->ev_out[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_out[1], cudaEventDisableTiming) != cudaSuccess ||
         cudaMalloc(&h->dstats, sizeof(int64_t) * NLB_STAT_COUNT) != cudaSuccess ||
-        cudaMalloc(&h->dcursor, sizeof(unsigned long long) * 16) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_work, cudaEventDisableTiming) != cudaSuccess ||
         cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
         delete h;
@@ -707,12 +705,11 @@ int nlb_create(nlb_handle** handle, int device) {
 
 int nlb_destroy(nlb_handle* h) {
     if (!h) return NLB_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     for (int i = 0; i < nlb_handle::NSLOT; ++i)
         if (h->dbuf[i]) cudaFree(h->dbuf[i]);
     if (h->dwork) cudaFree(h->dwork);
     if (h->dstats) cudaFree(h->dstats);
-    if (h->dcursor) cudaFree(h->dcursor);
     if (h->stream) cudaStreamDestroy(h->stream);
     for (int q = 0; q < 2; ++q) {
         if (h->pipe[q]) cudaStreamDestroy(h->pipe[q]);
@@ -825,8 +822,8 @@ int nlb_polynomial_fit_batch(nlb_handle* h, int64_t B, int npts, int order, int 
     if (npts <= 0 || order < 1 || order >= npts) return set_err(h, NLB_ERR_SIZE, "need 1 <= order < npts");
     const int nc = thru_zero ? order : order + 1;
     if (nc > POLY_MAX_COLS) return set_err(h, NLB_ERR_UNSUPPORTED, "polynomial fit: at most 8 fitted coefficients");
-    int rc = ensure_device(h);
-    if (rc) return rc;
+    NLB_DEVICE(h);
+    int rc = NLB_OK;
     if (B == 0) return NLB_OK;
     cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
     Staged ax, ay, ac, ast;
@@ -838,8 +835,7 @@ int nlb_polynomial_fit_batch(nlb_handle* h, int64_t B, int npts, int order, int 
     const size_t per_thread = sizeof(double) * (size_t)npts * (size_t)(nc + 1);
     const size_t smem_bytes = per_thread * 128;
     const size_t smem_max = 225 * 1024;                      // of the 227 KB a CTA may opt in to
-    static int force_global = -1;
-    if (force_global < 0) force_global = std::getenv("NLB_POLYFIT_GLOBAL") ? 1 : 0;   // tuning knob
+    static const int force_global = std::getenv("NLB_POLYFIT_GLOBAL") ? 1 : 0;   // tuning knob
     if (smem_bytes <= smem_max && !force_global) {
         // shared-memory workspace: persistent grid of the CTAs that fit (each SM has 228 KB)
         const int ctas_per_sm = (int)((228 * 1024) / (smem_bytes + 1024)) > 0 ? (int)((228 * 1024) / (smem_bytes + 1024)) : 1;
@@ -860,11 +856,10 @@ int nlb_polynomial_fit_batch(nlb_handle* h, int64_t B, int npts, int order, int 
         }
     } else {
         // global workspace, persistent grid at full occupancy
-        static int threads_per_sm = -1;
-        if (threads_per_sm < 0) {
+        static const int threads_per_sm = [] {
             const char* e = std::getenv("NLB_POLYFIT_THREADS_PER_SM");   // tuning knob, multiple of 128
-            threads_per_sm = e ? std::atoi(e) : 0;
-        }
+            return e ? std::atoi(e) : 0;
+        }();
         long long T;
         if (threads_per_sm > 0) {
             T = (long long)h->num_sms * threads_per_sm;
@@ -916,8 +911,8 @@ int nlb_polynomial_evaluate_batch(nlb_handle* h, int64_t B, int order, int npts,
     if (B < 0 || npts < 0 || (B > 0 && npts > 0 && (!x || !y || !coeffs)))
         return set_err(h, NLB_ERR_INVALID_ARGUMENT, "null argument or negative size");
     if (order < 0 || order > POLY_MAX_COLS) return set_err(h, NLB_ERR_UNSUPPORTED, "polynomial evaluate: order 0..8");
-    int rc = ensure_device(h);
-    if (rc) return rc;
+    NLB_DEVICE(h);
+    int rc = NLB_OK;
     if (B == 0 || npts == 0) return NLB_OK;
     cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
     Staged ax, ay, ac;
@@ -985,7 +980,7 @@ int nlb_vecfcn_eval_batch(nlb_handle* h, int fcn_id, int64_t B, int m, int n, co
     int sys_len, shared_len;
     int rc = check_sizes(h, fcn_id, &m, &n, &sys_len, &shared_len);
     if (rc) return rc;
-    if ((rc = ensure_device(h))) return rc;
+    NLB_DEVICE(h);
     if (B == 0) return NLB_OK;
     cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
     Staged ax, af, as, ash;
@@ -1022,7 +1017,7 @@ int nlb_jacobian_batch(nlb_handle* h, const nlb_params* params, int fcn_id, int6
     int sys_len, shared_len;
     int rc = check_sizes(h, fcn_id, &m, &n, &sys_len, &shared_len);
     if (rc) return rc;
-    if ((rc = ensure_device(h))) return rc;
+    NLB_DEVICE(h);
     if (B == 0) return NLB_OK;
     cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
     Staged ax, aj, as, ash;
@@ -1057,8 +1052,8 @@ int nlb_reduce_stats(nlb_handle* h, int64_t B, const nlb_iteration_behavior* ib,
     if (!h) return NLB_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(h->mu);
     if (!stats || B < 0) return set_err(h, NLB_ERR_INVALID_ARGUMENT, "null stats or B < 0");
-    int rc = ensure_device(h);
-    if (rc) return rc;
+    NLB_DEVICE(h);
+    int rc = NLB_OK;
     cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
     Staged aib, ast;
     if ((rc = stage_in(h, 4, ib, sizeof(nlb_iteration_behavior) * (size_t)B, true, s, &aib))) return rc;
@@ -1085,8 +1080,8 @@ int nlb_reduce_stats(nlb_handle* h, int64_t B, const nlb_iteration_behavior* ib,
 int nlb_measure_fp64_latency(nlb_handle* h, double* cycles4) {
     if (!h || !cycles4) return NLB_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(h->mu);
-    int rc = ensure_device(h);
-    if (rc) return rc;
+    NLB_DEVICE(h);
+    int rc = NLB_OK;
     double* dout = nullptr;
     NLB_CUDA(h, cudaMalloc(&dout, 8 * sizeof(double)));
     for (int rep = 0; rep < 2; ++rep) {
@@ -1104,8 +1099,8 @@ int nlb_measure_fp64_latency(nlb_handle* h, double* cycles4) {
 int nlb_measure_fp64_peak(nlb_handle* h, double* dfma_tflops, double* dadd_dmul_tflops) {
     if (!h) return NLB_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(h->mu);
-    int rc = ensure_device(h);
-    if (rc) return rc;
+    NLB_DEVICE(h);
+    int rc = NLB_OK;
     cudaDeviceProp prop;
     NLB_CUDA(h, cudaGetDeviceProperties(&prop, h->device));
     const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 20000;

@@ -67,21 +67,33 @@ def _rational(p, q, t):
     return num / (1.0 + t[None, :] * den)
 
 
-def c4_lm_rational(B, m=4096, seed=4, noise=0.0):
-    """C4: LM curve fit m x 16, rational 7/8 model on t in [-1,1]; x0 = truth*(1 + 0.1 U(-1,1))."""
+def c4_lm_rational(B, m=4096, seed=4, noise=0.0, with_y=True):
+    """C4: LM curve fit m x 16, rational 7/8 model on t in [-1,1]; x0 = truth*(1 + 0.1 U(-1,1)).
+
+    with_y=False leaves `args` (the m x B observations, 2 GB at the BASELINE batch) to the caller, who forms them
+    from `truth` with the same Horner recurrence as `_rational` (bench.py does it on the device); x0 is then drawn
+    from the stream position of the noise-free workload."""
     rng = np.random.default_rng(seed)
     t = np.linspace(-1.0, 1.0, m)
     p = rng.uniform(-1.0, 1.0, size=(8, B))
     q = rng.uniform(-0.1, 0.1, size=(8, B))
     truth = np.concatenate([p, q], axis=0)
-    y = _rational(p, q, t).T  # (m, B)
-    if noise:
-        y = y + noise * rng.standard_normal(y.shape)
+    y = None
+    if with_y:
+        y = _rational(p, q, t).T  # (m, B)
+        if noise:
+            y = y + noise * rng.standard_normal(y.shape)
+        y = np.ascontiguousarray(y)
     x0 = truth * (1.0 + 0.1 * rng.uniform(-1.0, 1.0, size=truth.shape))
-    return dict(name="C4", solver="least_squares", fcn="rational_7_8", m=m, n=16,
-                x0=np.ascontiguousarray(x0), args=np.ascontiguousarray(y), shared=t,
+    return dict(name="C4" if not noise else "C4N", solver="least_squares", fcn="rational_7_8", m=m, n=16,
+                x0=np.ascontiguousarray(x0), args=y, shared=t, truth=truth, noise=noise,
                 settings={"set_max_fcn_evals": 1000},
                 bytes_per_system=_bytes(m, 16, m))
+
+
+def c4n_lm_rational(B, m=4096, seed=4, with_y=True):
+    """C4N: the C4 fits with Gaussian noise of sigma = 1e-3 on the observations (SURVEY.md 8d variant)."""
+    return c4_lm_rational(B, m=m, seed=seed, noise=1e-3, with_y=with_y)
 
 
 def c5_broyden_rosenbrock(B, n=64, seed=5):
@@ -136,6 +148,7 @@ WORKLOADS = {
     "C2": c2_broyden_2x2,
     "C3": c3_newton_powell,
     "C4": c4_lm_rational,
+    "C4N": c4n_lm_rational,
     "C5": c5_broyden_rosenbrock,
     "LM4": lm_expdecay4,
     "CLS1": cls1_bounded_polyfit,

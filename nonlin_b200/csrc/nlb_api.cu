@@ -14,6 +14,7 @@
 #include "coop_kernels.cuh"
 #include "launch_cfg.cuh"
 #include "polyfit.cuh"
+#include "quad_lm.cuh"
 #include "scalar_solvers.cuh"
 #include "tps_cls.cuh"
 #include "tps_lm.cuh"
@@ -429,6 +430,30 @@ int launch_tps_lm_smem(nlb_handle* h, const DevParams& p, long long nsys, long l
     return NLB_OK;
 }
 
+// Levenberg-Marquardt for the small curve fits: four lanes per system, Jacobian in registers (quad_lm.cuh).
+// Bit-identical to the thread-per-system kernel; NLB_LM_QUAD=0 / 1 forces one or the other (re-measurement).
+#ifndef NLB_LM_QUAD_DEFAULT
+#define NLB_LM_QUAD_DEFAULT 0      // measured on B200 (2^20 C1 fits): quad kernel v1 14.1 ms, thread-per-system 6.9 ms
+#endif
+template <class F>
+int launch_qlm(nlb_handle* h, const DevParams& p, long long nsys, long long B, double* x, double* fvec,
+               const double* sys, const double* shared, nlb_iteration_behavior* ib, int32_t* status, cudaStream_t s) {
+    static const int use_quad = [] {
+        const char* e = std::getenv("NLB_LM_QUAD");
+        return e ? std::atoi(e) : NLB_LM_QUAD_DEFAULT;
+    }();
+    if (!use_quad) return launch_tps_lm_smem<F>(h, p, nsys, B, x, fvec, sys, shared, ib, status, s);
+    if (nsys == 0) return NLB_OK;
+    constexpr size_t smem = QlmSmem<F>::BYTES;
+    KernelCfg cfg;
+    NLB_CUDA(h, kernel_cfg<qlm_kernel<F>>(QLM_BLOCK, smem, &cfg));
+    const unsigned grid = (unsigned)((nsys + QLM_QUADS - 1) / QLM_QUADS);
+    qlm_kernel<F><<<grid, QLM_BLOCK, smem, s>>>(p, nsys, B, x, fvec, sys, shared, ib, status);
+    ++h->launches;
+    NLB_CUDA(h, cudaGetLastError());
+    return NLB_OK;
+}
+
 #define NLB_SQUARE_FCNS(X) \
     X(Misc2Fcn) X(Misc2FcnA) X(PoorlyScaled2Fcn) X(PowellBadlyScaled) X(Misc2Fcn01) X(Polar) X(PolarScaled)
 #define NLB_FIXED_FCNS(X) NLB_SQUARE_FCNS(X) X(LsqPolyFit)
@@ -448,7 +473,7 @@ int dispatch_tps(nlb_handle* h, int fcn_id, const DevParams& p, long long nsys, 
 #undef X
         case LsqPolyFit::ID:
             if constexpr (SOLVER == SOLVER_LM)
-                return launch_tps_lm_smem<LsqPolyFit>(h, p, nsys, B, x, fvec, sys, shared, ib, status, s);
+                return launch_qlm<LsqPolyFit>(h, p, nsys, B, x, fvec, sys, shared, ib, status, s);
             else
                 return set_err(h, NLB_ERR_SIZE, "Newton / quasi-Newton need m == n");
         default: return set_err(h, NLB_ERR_UNSUPPORTED, "no thread-per-system kernel for this residual");

@@ -178,6 +178,12 @@ struct LsqPolyFit {
         }
     }
     NLB_DEV static void jac(const double (&)[4], JacView<21>, const SysCtx&) {}
+    // row-wise form of eval() for the kernels that split a system's rows over several lanes (quad_lm.cuh):
+    // the same expression, one observation at a time
+    NLB_DEV static double abscissa(int i, const double*) { return kPolyFitXp[i]; }
+    NLB_DEV static double row(const double (&x)[4], double xp, double yp) {
+        return x[0] * ((xp * xp) * xp) + x[1] * (xp * xp) + x[2] * xp + x[3] - yp;
+    }
 };
 
 // ---- run-time sized families (cooperative kernels) --------------------------------------

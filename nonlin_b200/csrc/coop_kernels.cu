@@ -5,13 +5,22 @@
 #include "coop_broyden.cuh"
 #include "coop_lm.cuh"
 #include "coop_lm_cta.cuh"
+#include "tall_lm.cuh"
+
+#include <cstdlib>
 
 namespace nlb {
 
 namespace {
 
 enum { SOLVER_LM = 0, SOLVER_NEWTON = 1, SOLVER_BROYDEN = 2 };
-constexpr int WLM_MIN_M = 512;   // rows from which the CTA-per-system LM kernel is used
+constexpr int WLM_MIN_M = 512;   // rows from which the CTA-per-system LM kernels are used
+#ifndef NLB_TLM_SEG
+#define NLB_TLM_SEG 64           // rows per TMA segment of tall_lm.cuh (= producer threads per CTA)
+#endif
+#ifndef NLB_TLM_STAGES
+#define NLB_TLM_STAGES 4         // stages of its input ring
+#endif
 
 template <class F, int N>
 int launch_broyden(const DevParams& p, long long nsys, long long B, double* x, double* fvec, const double* sys, const double* shared,
@@ -137,6 +146,52 @@ int launch_wlm(const DevParams& p, long long ntot, long long B, int m, double* x
     return NLB_OK;
 }
 
+// Tall systems, TMA-streamed (tall_lm.cuh): persistent CTAs of 32 + S threads, several per SM.
+template <class F, int N, int S, int NST>
+int launch_tlm(const DevParams& p, long long ntot, long long B, int m, double* x, double* fvec, const double* sys,
+               const double* shared, nlb_iteration_behavior* ib, int32_t* status, cudaStream_t s, int64_t* launches) {
+    using C = TlmCfg<N, S, NST>;
+    KernelCfg cfg;
+    if (kernel_cfg<tlm_kernel<F, N, S, NST>>(C::NT, C::BYTES, &cfg) != cudaSuccess) return NLB_ERR_CUDA;
+    static const int per_sm_override = [] {
+        const char* e = std::getenv("NLB_TLM_CTAS_PER_SM");      // tuning knob
+        return e ? std::atoi(e) : 0;
+    }();
+    int per_sm = cfg.ctas_per_sm;
+    if (per_sm_override > 0 && per_sm_override < per_sm) per_sm = per_sm_override;
+    long long grid = ntot;
+    if (grid > (long long)cfg.num_sms * per_sm) grid = (long long)cfg.num_sms * per_sm;
+    const int MP = (m + S - 1) / S * S;
+    const size_t per_cta = (size_t)(N + 3) * (size_t)MP;         // doubles
+    double* ws = nullptr;
+    if (cudaMallocAsync((void**)&ws, (per_cta * (size_t)grid + (size_t)MP + 8) * sizeof(double), s) != cudaSuccess)
+        return NLB_ERR_CUDA;
+    double* tpad = ws + per_cta * (size_t)grid;                  // abscissae padded to whole segments
+    unsigned long long* cursor = reinterpret_cast<unsigned long long*>(tpad + MP);
+    if (cudaMemsetAsync(tpad, 0, ((size_t)MP + 8) * sizeof(double), s) != cudaSuccess ||
+        cudaMemcpyAsync(tpad, shared, (size_t)m * sizeof(double), cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
+        cudaFreeAsync(ws, s);
+        return NLB_ERR_CUDA;
+    }
+    tlm_kernel<F, N, S, NST><<<(unsigned)grid, C::NT, C::BYTES, s>>>(p, B, ntot, m, MP, x, fvec, sys, tpad, ib, status, ws, cursor);
+    ++*launches;
+    if (cudaGetLastError() != cudaSuccess) { cudaFreeAsync(ws, s); return NLB_ERR_CUDA; }
+    if (cudaFreeAsync(ws, s) != cudaSuccess) return NLB_ERR_CUDA;
+    return NLB_OK;
+}
+
+// m >= WLM_MIN_M: the TMA-streamed kernel; NLB_TALL_LM=wlm selects the previous CTA-per-system kernel (re-measurement)
+template <class F>
+int launch_tall(const DevParams& p, long long ntot, long long B, int m, double* x, double* fvec, const double* sys,
+                const double* shared, nlb_iteration_behavior* ib, int32_t* status, cudaStream_t s, int64_t* launches) {
+    static const int use_wlm = [] {
+        const char* e = std::getenv("NLB_TALL_LM");
+        return (e && e[0] == 'w') ? 1 : 0;
+    }();
+    if (use_wlm) return launch_wlm<F, 16>(p, ntot, B, m, x, fvec, sys, shared, ib, status, s, launches);
+    return launch_tlm<F, 16, NLB_TLM_SEG, NLB_TLM_STAGES>(p, ntot, B, m, x, fvec, sys, shared, ib, status, s, launches);
+}
+
 }  // namespace
 
 int launch_coop_lm(int fcn_id, const DevParams& p, long long nsys, long long B, int m, int n, double* x, double* fvec, const double* sys,
@@ -146,10 +201,10 @@ int launch_coop_lm(int fcn_id, const DevParams& p, long long nsys, long long B, 
         // tall fits: one CTA per system (a lone slow system costs ~1 ms per iteration instead of ~17 ms);
         // short ones: one lane per system (more systems in flight)
         case FCN_RATIONAL_7_8:
-            if (m >= WLM_MIN_M) return launch_wlm<Rational78, 16>(p, nsys, B, m, x, fvec, sys, shared, ib, status, s, launches);
+            if (m >= WLM_MIN_M) return launch_tall<Rational78>(p, nsys, B, m, x, fvec, sys, shared, ib, status, s, launches);
             return launch_lm<Rational78, 16>(p, nsys, B, m, x, fvec, sys, shared, ib, status, s, launches);
         case FCN_EXP_SUM_8:
-            if (m >= WLM_MIN_M) return launch_wlm<ExpSum8, 16>(p, nsys, B, m, x, fvec, sys, shared, ib, status, s, launches);
+            if (m >= WLM_MIN_M) return launch_tall<ExpSum8>(p, nsys, B, m, x, fvec, sys, shared, ib, status, s, launches);
             return launch_lm<ExpSum8, 16>(p, nsys, B, m, x, fvec, sys, shared, ib, status, s, launches);
         case FCN_EXP_DECAY_4: return launch_lm<ExpDecay4, 4>(p, nsys, B, m, x, fvec, sys, shared, ib, status, s, launches);
         default: return NLB_ERR_UNSUPPORTED;

@@ -69,7 +69,8 @@ using LaneIVec = SIVec<32>;
 template <int N, class V>
 NLB_DEV double clm_norm2(const V& v) {
     Norm2 acc;
-    for (int i = 0; i < N; ++i) acc.add(v[i]);
+#pragma unroll 1
+    for (int i = 0; i < N; ++i) acc.add(v[i]);      // rolled: a dozen call sites x N inlined divisions otherwise
     return acc.value();
 }
 

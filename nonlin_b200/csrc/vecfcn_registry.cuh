@@ -203,15 +203,37 @@ struct Rational78 {
         den = 1.0 + t * den;
         return num / den - y;
     }
+    // residual(x with x[c] replaced by xc, t, y): the same operations in the same order, the replaced parameter chosen
+    // by a select so that a rolled loop over c keeps x in registers (forward-difference columns of tall_lm.cuh)
+    NLB_DEV static double residual_pert(const double* x, int c, double xc, double t, double y) {
+        double num = (c == 7) ? xc : x[7];
+#pragma unroll
+        for (int k = 6; k >= 0; --k) num = num * t + ((c == k) ? xc : x[k]);
+        double den = (c == 15) ? xc : x[15];
+#pragma unroll
+        for (int k = 14; k >= 8; --k) den = den * t + ((c == k) ? xc : x[k]);
+        den = 1.0 + t * den;
+        return num / den - y;
+    }
 };
 
 // sum of 8 exponentials, x = [a0..a7, b0..b7]         (BASELINE config 4 throughput model)
 struct ExpSum8 {
     static constexpr int ID = FCN_EXP_SUM_8, N = 16;
-    NLB_DEV static double residual(const double* x, double t, double y) {
+    NLB_DEV static double residual(const double* x, double t, double y) { return residual_pert(x, -1, 0.0, t, y); }
+    // one exponential per trip of a rolled loop (eight inlined copies of nl_exp cost 20 k instructions per kernel);
+    // the parameters are picked out of registers by select chains
+    NLB_DEV static double residual_pert(const double* x, int c, double xc, double t, double y) {
         double s = 0.0;
+#pragma unroll 1
+        for (int k = 0; k < 8; ++k) {
+            double a = x[0], b = x[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s += x[k] * nl_exp(-(x[8 + k] * t));
+            for (int u = 1; u < 8; ++u) { a = (k == u) ? x[u] : a; b = (k == u) ? x[8 + u] : b; }
+            a = (c == k) ? xc : a;
+            b = (c == 8 + k) ? xc : b;
+            s += a * nl_exp(-(b * t));
+        }
         return s - y;
     }
 };

@@ -26,3 +26,11 @@ for nsel in (1, 4, 32):
     for me in (50, 100):
         dt, ibs = run(xs, ar, me)
         print("lone group of %d straggler(s), maxeval=%d: %.3fs -> %.2f ms per evaluation (njac %s)" % (nsel, me, dt, dt / me * 1e3, ibs["jacobian_count"][:4]))
+# throughput regime: the same straggler replicated so that every CTA does identical work
+for nrep in (148, 444, 592, 1184, 2368):
+    idx = torch.from_numpy(np.resize(slow[:8], nrep)).cuda()
+    xs = x0[:, idx].contiguous(); ar = args[:, idx].contiguous()
+    dt, ibs = run(xs, ar, 50)
+    nj = int(ibs["jacobian_count"].sum())
+    print("%d replicated stragglers, maxeval=50: %.3fs -> %.1f us per outer iteration per system amortised, %.0f outer iterations/s (njac/system %d)"
+          % (nrep, dt, dt / nj * 1e6, nj / dt, nj // nrep))

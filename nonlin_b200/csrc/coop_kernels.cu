@@ -19,7 +19,7 @@ constexpr int WLM_MIN_M = 512;   // rows from which the CTA-per-system LM kernel
 #define NLB_TLM_SEG 64           // rows per TMA segment of tall_lm.cuh (= producer threads per CTA)
 #endif
 #ifndef NLB_TLM_STAGES
-#define NLB_TLM_STAGES 4         // stages of its input ring
+#define NLB_TLM_STAGES 3         // stages of its input ring (measured: 4 stages were no faster, and cost a resident CTA)
 #endif
 
 template <class F, int N>

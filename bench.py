@@ -49,7 +49,7 @@ HEADLINE = "C1"
 BATCH = {"C1": 1 << 20, "C2": 1 << 20, "C3": 1 << 20, "C4": 65536, "C4N": 65536, "C5": 16384, "LM4": 1 << 20,
          "CLS1": 1 << 20, "CLS2": 1 << 20}
 EXTRA_CONFIGS = ("C2", "C3", "C4", "C4N", "C5")
-KERNEL = {"C1": "qlm_kernel<LsqPolyFit> (4 lanes per system)", "C2": "tps_solve_kernel<Misc2Fcn, Broyden>",
+KERNEL = {"C1": "tps_solve_kernel<LsqPolyFit, LM>", "C2": "tps_solve_kernel<Misc2Fcn, Broyden>",
           "C3": "tps_newton_refill_kernel<PowellBadlyScaled>", "C4": "tlm_kernel<Rational78, 16>",
           "C4N": "tlm_kernel<Rational78, 16>", "C5": "coop_broyden_kernel<ExtRosenbrock, 64>",
           "LM4": "coop_lm_kernel<ExpDecay4, 4>", "CLS1": "tps_cls_kernel<LsqPolyFit>", "CLS2": "tps_cls_kernel<Misc2Fcn>"}

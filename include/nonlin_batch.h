@@ -126,7 +126,8 @@ const char* nlb_vecfcn_name(int fcn_id);            /* NULL if unknown */
 int nlb_vecfcn_info(int fcn_id, int* m, int* n, int* sys_len, int* shared_len, int* has_jacobian);
 
 /* least_squares_solver%solve  (lss_solve, src/nonlin_least_squares.f90:118-391) over B systems.
- * x in/out, fvec out, ib / status out (either may be NULL). stream: cudaStream_t, or NULL for the
+ * x in/out, fvec out, ib / status out (fvec, ib and status may each be NULL: an output that is not asked for is not
+ * copied back - for host buffers the call is PCIe-bound and x + status are 20 of the 64 bytes per 2x2 system). stream: cudaStream_t, or NULL for the
  * handle's own stream (pass cudaStreamLegacy to name the legacy default stream).  Asynchronous when every pointer is a device pointer; synchronous otherwise. */
 int nlb_least_squares_solve_batch(nlb_handle* handle, const nlb_params* params, int fcn_id, int64_t B, int m, int n,
                                   double* x, double* fvec, const double* sys, const double* shared,
@@ -237,6 +238,20 @@ int nlb_jacobian_batch(nlb_handle* handle, const nlb_params* params, int fcn_id,
  * the path. */
 int nlb_reduce_stats(nlb_handle* handle, int64_t B, const nlb_iteration_behavior* ib, const int32_t* status,
                      int64_t* stats, void* stream);
+
+/* One batch over several GPUs of ONE process (the caller shape of a Fortran host: a single `solve` call, reference
+ * src/nonlin_multi_eqn_mult_var.f90:94-119; no launcher, no MPI).  handles[ndev]: one handle per device.  The batch
+ * shards by contiguous system ranges (sizes differ by at most one); every device solves its range on its own host
+ * thread - there is no data-path collective - and the convergence statistics are combined with one NCCL all-reduce
+ * (SUM; MAX for NLB_STAT_MAX_ITER) over NVLink into stats[NLB_STAT_COUNT] (host; may be NULL: no collective at all).
+ * All data pointers are HOST buffers laid out as for the single-device calls; fvec, ib and status may be NULL.
+ * solver: one of NLB_SOLVER_*.  NCCL is loaded at run time (libnccl.so.2) and only when ndev > 1 and stats != NULL. */
+#define NLB_SOLVER_LEAST_SQUARES 0
+#define NLB_SOLVER_NEWTON 1
+#define NLB_SOLVER_QUASI_NEWTON 2
+int nlb_solve_sharded(nlb_handle* const* handles, int ndev, int solver, const nlb_params* params, int fcn_id, int64_t B,
+                      int m, int n, double* x, double* fvec, const double* sys, const double* shared,
+                      nlb_iteration_behavior* ib, int32_t* status, int64_t* stats);
 
 /* Measured FP64 throughput of this GPU (roofline denominator): dependent-chain-free DFMA and
  * DADD/DMUL micro-kernels, TFLOP/s.  The parity build issues no DFMA, so its ceiling is the

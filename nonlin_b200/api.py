@@ -395,8 +395,11 @@ class equation_solver:
         p.use_analytic_jacobian = int(fcn.is_jacobian_defined())
         return p
 
-    def solve(self, fcn, x, fvec=None, ib=None, args=None, status=None, stream=None):
+    def solve(self, fcn, x, fvec=None, ib=None, args=None, status=None, stream=None, want_fvec=True):
         """Solve the B systems in x (n, B) in place. Returns the per-system status array.
+
+        want_fvec=False (with fvec=None): the residuals are not returned - for host buffers the call is PCIe-bound
+        and fvec is most of what travels back.
 
         `stream` (a raw cudaStream_t integer) overrides the stream choice: by default CUDA tensors
         run on torch's current stream and host arrays on the engine's own stream.
@@ -411,9 +414,10 @@ class equation_solver:
             raise NonlinError(_lib.NLB_ERR_SIZE, "x must be (n, B)")
         B = x.shape[1]
         _check_f64("x", x, (n, B))
-        if fvec is None:
+        if fvec is None and want_fvec:
             fvec = _empty_like(x, (m, B))
-        _check_f64("fvec", fvec, (m, B))
+        if fvec is not None:
+            _check_f64("fvec", fvec, (m, B))
         if args is not None:
             _check_f64("args", args, (fcn._info["sys_len"], B))
         if status is None:
@@ -438,11 +442,41 @@ class equation_solver:
         """Solver-specific arguments that follow `params` in the C entry point (none for most solvers)."""
         return ()
 
+    _sharded_kind = None
+
+    def solve_sharded(self, engines, fcn, x, fvec=None, ib=None, args=None, status=None, want_stats=True):
+        """One HOST batch over several GPUs of this process (nlb_solve_sharded): contiguous system ranges, one host
+        thread and one engine handle per device, no data-path collective; the convergence statistics are combined with
+        one NCCL all-reduce.  Returns (status, stats dict or None)."""
+        if self._sharded_kind is None:
+            raise NonlinError(_lib.NLB_ERR_UNSUPPORTED, "no sharded entry point for this solver")
+        if not fcn.is_fcn_defined():
+            raise NonlinError(_lib.NLB_ERR_UNKNOWN_FCN, "no residual set (NL_UNDEFINED_FUNCTION_ERROR)")
+        m, n = fcn.get_equation_count(), fcn.get_variable_count()
+        B = x.shape[1]
+        for name, a, shape in (("x", x, (n, B)), ("fvec", fvec, (m, B)), ("args", args, (fcn._info["sys_len"], B))):
+            if a is not None:
+                if _is_torch(a) and a.is_cuda:
+                    raise NonlinError(_lib.NLB_ERR_INVALID_ARGUMENT, "a sharded solve takes host buffers")
+                _check_f64(name, a, shape)
+        if status is None:
+            status = np.zeros(B, dtype=np.int32)
+        _check_i32("status", status, B)
+        _check_i32("ib", ib, B, 7)
+        hs = (C.c_void_p * len(engines))(*[e._h for e in engines])
+        stats = np.zeros(NLB_STAT_COUNT, dtype=np.int64) if want_stats else None
+        p = self._params(fcn)
+        rc = _LIB.nlb_solve_sharded(hs, len(engines), self._sharded_kind, C.byref(p), fcn._fcn_id, B, m, n, _ptr(x), _ptr(fvec),
+                                    _ptr(args), _ptr(fcn._shared), _ptr(ib), _ptr(status), _ptr(stats))
+        engines[0].check(rc)
+        return status, (None if stats is None else {k: int(stats[i]) for i, k in enumerate(NLB_STAT_NAMES)})
+
 
 class least_squares_solver(equation_solver):
     """Levenberg-Marquardt (reference src/nonlin_least_squares.f90:20-31, lss_solve :118-391)."""
 
     _entry = "nlb_least_squares_solve_batch"
+    _sharded_kind = 0      # NLB_SOLVER_LEAST_SQUARES
 
     def __init__(self, engine=None):
         super().__init__(engine)
@@ -499,6 +533,7 @@ class constrained_least_squares_solver(constrained_equation_solver):
     """Bounded trust-region dogleg (reference src/nonlin_least_squares.f90:50-75, cls_solve :938-1176)."""
 
     _entry = "nlb_constrained_least_squares_solve_batch"
+    _sharded_kind = None
 
     def __init__(self, engine=None):
         super().__init__(engine)
@@ -580,6 +615,7 @@ class quasi_newton_solver(line_search_solver):
     """Broyden's method with QR rank-1 updates (reference src/nonlin_solve.f90:43-58, qns_solve :156-425)."""
 
     _entry = "nlb_quasi_newton_solve_batch"
+    _sharded_kind = 2      # NLB_SOLVER_QUASI_NEWTON
 
     def __init__(self, engine=None):
         super().__init__(engine)
@@ -601,6 +637,7 @@ class newton_solver(line_search_solver):
     """Newton's method with LU (reference src/nonlin_solve.f90:60-67, ns_solve :452-638)."""
 
     _entry = "nlb_newton_solve_batch"
+    _sharded_kind = 1      # NLB_SOLVER_NEWTON
 
 
 class value_pair:

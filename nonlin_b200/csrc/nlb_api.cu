@@ -10,6 +10,9 @@
 #include <string>
 
 #include <cstdlib>
+#include <dlfcn.h>
+#include <thread>
+#include <vector>
 
 #include "coop_kernels.cuh"
 #include "launch_cfg.cuh"
@@ -79,6 +82,28 @@ bool is_device_ptr(const void* p) {
     if (e != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
+
+bool is_device_ptr_nonnull(const void* p) { return p != nullptr && is_device_ptr(p); }
+
+// NVTX ranges around the phases of a host-buffer solve (H2D / kernel / D2H), resolved at run time from libnvToolsExt
+// so that the library has no link-time dependency on it; no-ops when no profiler library is present.
+struct NvtxApi {
+    int (*push)(const char*) = nullptr;
+    int (*pop)() = nullptr;
+    NvtxApi() {
+        for (const char* name : {"libnvToolsExt.so.1", "libnvToolsExt.so"}) {
+            if (void* lib = dlopen(name, RTLD_LAZY | RTLD_GLOBAL)) {
+                push = reinterpret_cast<int (*)(const char*)>(dlsym(lib, "nvtxRangePushA"));
+                pop = reinterpret_cast<int (*)()>(dlsym(lib, "nvtxRangePop"));
+                if (push && pop) return;
+            }
+        }
+        push = nullptr; pop = nullptr;
+    }
+};
+const NvtxApi& nvtx_api() { static const NvtxApi api; return api; }
+void nvtx_push(const char* name) { if (nvtx_api().push) nvtx_api().push(name); }
+void nvtx_pop() { if (nvtx_api().pop) nvtx_api().pop(); }
 
 // One argument of a call: the caller's pointer and the device pointer the kernel uses.
 struct Staged {
@@ -584,12 +609,17 @@ int check_sizes(nlb_handle* h, int fcn_id, int* m, int* n, int* sys_len, int* sh
     return NLB_OK;
 }
 
+// r0 / rcnt: solve only systems [r0, r0 + rcnt) of the batch (rcnt < 0: all of it).  A range call takes HOST buffers
+// only and keeps a compact copy of its shard on the device (this is how nlb_solve_sharded spreads one batch over
+// several GPUs).  want_stats: leave the shard's convergence statistics in h->dstats (device) before returning.
 int solve_batch(nlb_handle* h, int solver, const nlb_params* params, int fcn_id, int64_t B, int m, int n, double* x,
                 double* fvec, const double* sys, const double* shared, nlb_iteration_behavior* ib, int32_t* status,
-                void* stream, const DevCls* cls = nullptr) {
+                void* stream, const DevCls* cls = nullptr, int64_t r0 = 0, int64_t rcnt = -1, bool want_stats = false) {
     if (!h) return NLB_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(h->mu);
-    if (!params || B < 0 || (B > 0 && (!x || !fvec))) return set_err(h, NLB_ERR_INVALID_ARGUMENT, "null argument or B < 0");
+    if (!params || B < 0 || (B > 0 && !x)) return set_err(h, NLB_ERR_INVALID_ARGUMENT, "null argument or B < 0");
+    const bool ranged = rcnt >= 0;
+    if (ranged && (r0 < 0 || r0 + rcnt > B)) return set_err(h, NLB_ERR_INVALID_ARGUMENT, "range outside the batch");
     int sys_len, shared_len;
     int rc = check_sizes(h, fcn_id, &m, &n, &sys_len, &shared_len);
     if (rc) return rc;
@@ -599,14 +629,42 @@ int solve_batch(nlb_handle* h, int solver, const nlb_params* params, int fcn_id,
     if (sys_len > 0 && B > 0 && !sys) return set_err(h, NLB_ERR_INVALID_ARGUMENT, "this residual needs per-system data");
     if (shared_len > 0 && B > 0 && !shared) return set_err(h, NLB_ERR_INVALID_ARGUMENT, "this residual needs shared data");
     NLB_DEVICE(h);
-    if (B == 0) return NLB_OK;
+    const int64_t nb = ranged ? rcnt : B;          // systems solved by this call
+    if (nb == 0) {
+        if (want_stats) NLB_CUDA(h, cudaMemsetAsync(h->dstats, 0, sizeof(int64_t) * NLB_STAT_COUNT, h->stream));
+        return NLB_OK;
+    }
     cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    if (ranged) {
+        if (is_device_ptr_nonnull(x) || is_device_ptr_nonnull(fvec) || is_device_ptr_nonnull(sys) ||
+            is_device_ptr_nonnull(ib) || is_device_ptr_nonnull(status))
+            return set_err(h, NLB_ERR_INVALID_ARGUMENT, "a sharded solve takes host buffers");
+        x += r0;
+        if (fvec) fvec += r0;
+        if (sys) sys += r0;
+        if (ib) ib += r0;
+        if (status) status += r0;
+    }
+    const int64_t Bh = B;                          // SoA stride of the caller's arrays
+    const int64_t Bd = ranged ? nb : B;            // SoA stride of the device arrays
+    // fvec is optional (NULL: the residuals stay in a device scratch buffer and are not copied back)
+    const bool fvec_scratch = fvec == nullptr;
+    if (fvec_scratch) {
+        const size_t need = sizeof(double) * (size_t)m * (size_t)Bd;
+        if (h->dcap[7] < need) {
+            if (h->dbuf[7]) NLB_CUDA(h, cudaFree(h->dbuf[7]));
+            h->dbuf[7] = nullptr; h->dcap[7] = 0;
+            NLB_CUDA(h, cudaMalloc(&h->dbuf[7], need));
+            h->dcap[7] = need;
+        }
+        fvec = (double*)h->dbuf[7];
+    }
 
     // Arguments are SoA arrays of `rows` x B elements; host-resident ones get a device twin.
     struct Arg { Staged st; size_t rows, elem; bool in, out; };
     Arg a[5] = {
         {{}, (size_t)n, sizeof(double), true, true},                       // x
-        {{}, (size_t)m, sizeof(double), false, true},                      // fvec
+        {{}, (size_t)m, sizeof(double), false, !fvec_scratch},             // fvec
         {{}, (size_t)sys_len, sizeof(double), true, false},                // per-system data
         {{}, 1, sizeof(nlb_iteration_behavior), false, true},              // ib
         {{}, 1, sizeof(int32_t), false, true},                             // status
@@ -615,7 +673,7 @@ int solve_batch(nlb_handle* h, int solver, const nlb_params* params, int fcn_id,
     const int slot[5] = {0, 1, 2, 4, 5};
     bool any_staged = false;
     for (int i = 0; i < 5; ++i) {
-        if ((rc = stage_in(h, slot[i], user[i], a[i].rows * a[i].elem * (size_t)B, false, s, &a[i].st))) return rc;
+        if ((rc = stage_in(h, slot[i], user[i], a[i].rows * a[i].elem * (size_t)Bd, false, s, &a[i].st))) return rc;
         any_staged = any_staged || a[i].st.staged;
     }
     Staged ash;
@@ -634,60 +692,83 @@ int solve_batch(nlb_handle* h, int solver, const nlb_params* params, int fcn_id,
         int r;
         if (solver == SOLVER_CLS) {
             r = (fi.m != 0 && fi.n != 0)
-                    ? dispatch_cls(h, fcn_id, p, *cls, cnt, B, dx, df, ds, dsh, dib, dst, st)
+                    ? dispatch_cls(h, fcn_id, p, *cls, cnt, Bd, dx, df, ds, dsh, dib, dst, st)
                     : set_err(h, NLB_ERR_UNSUPPORTED, "constrained least squares: fixed-size residuals only");
         } else if (fi.m != 0 && fi.n != 0) {
             switch (solver) {
-                case SOLVER_LM: r = dispatch_tps<SOLVER_LM>(h, fcn_id, p, cnt, B, dx, df, ds, dsh, dib, dst, st); break;
-                case SOLVER_NEWTON: r = dispatch_tps<SOLVER_NEWTON>(h, fcn_id, p, cnt, B, dx, df, ds, dsh, dib, dst, st); break;
-                default: r = dispatch_tps<SOLVER_BROYDEN>(h, fcn_id, p, cnt, B, dx, df, ds, dsh, dib, dst, st);
+                case SOLVER_LM: r = dispatch_tps<SOLVER_LM>(h, fcn_id, p, cnt, Bd, dx, df, ds, dsh, dib, dst, st); break;
+                case SOLVER_NEWTON: r = dispatch_tps<SOLVER_NEWTON>(h, fcn_id, p, cnt, Bd, dx, df, ds, dsh, dib, dst, st); break;
+                default: r = dispatch_tps<SOLVER_BROYDEN>(h, fcn_id, p, cnt, Bd, dx, df, ds, dsh, dib, dst, st);
             }
         } else {
-            r = launch_coop_solve(solver, fcn_id, p, cnt, B, m, n, dx, df, ds, dsh, dib, dst, st, &h->launches);
+            r = launch_coop_solve(solver, fcn_id, p, cnt, Bd, m, n, dx, df, ds, dsh, dib, dst, st, &h->launches);
             if (r == NLB_ERR_UNSUPPORTED) return set_err(h, r, "no cooperative kernel for this (solver, residual, size)");
             if (r == NLB_ERR_CUDA) return set_err(h, r, "cooperative kernel launch", cudaGetLastError());
         }
         return r;
     };
 
-    if (!any_staged) return launch(0, B, s);          // all-device call: one asynchronous launch on the caller's stream
+    auto shard_stats = [&](cudaStream_t st) -> int {
+        NLB_CUDA(h, cudaMemsetAsync(h->dstats, 0, sizeof(int64_t) * NLB_STAT_COUNT, st));
+        unsigned grid = (unsigned)((nb + 255) / 256);
+        const unsigned cap = (unsigned)(h->num_sms > 0 ? h->num_sms : 148) * 4u;
+        if (grid > cap) grid = cap;
+        stats_kernel<<<grid, 256, 0, st>>>(nb, (const nlb_iteration_behavior*)a[3].st.dev, (const int32_t*)a[4].st.dev,
+                                           (unsigned long long*)h->dstats);
+        ++h->launches;
+        NLB_CUDA(h, cudaGetLastError());
+        return NLB_OK;
+    };
+
+    if (!any_staged) {                                // all-device call: one asynchronous launch on the caller's stream
+        if ((rc = launch(0, nb, s))) return rc;
+        return want_stats ? shard_stats(s) : NLB_OK;
+    }
 
     // Host-resident batch: split it into chunks and pipeline H2D copy / kernel / D2H copy on two
     // streams, so that the two copy engines and the SMs overlap (the path is PCIe-bound).
     // Measured on B200 (C2, 2^20 systems, 67 MB back over PCIe; raw pinned D2H of the same bytes 1.2-1.4 ms):
     // 4 chunks 1.58 ms, 8 chunks 1.68 ms, 16 chunks 1.83 ms, 32 chunks 2.14 ms - per-copy overhead outweighs the
     // shorter pipeline fill beyond 4.
-    int nchunk = B >= (1 << 18) ? 4 : (B >= (1 << 15) ? 2 : 1);
+    int nchunk = nb >= (1 << 18) ? 4 : (nb >= (1 << 15) ? 2 : 1);
     static const int chunk_override = [] {
         const char* e = std::getenv("NLB_HOST_CHUNKS");      // tuning knob
         return e ? std::atoi(e) : 0;
     }();
     if (chunk_override > 0) nchunk = chunk_override;
-    const long long chunk = (B + nchunk - 1) / nchunk;
+    const long long chunk = (nb + nchunk - 1) / nchunk;
     NLB_CUDA(h, cudaEventRecord(h->ev_in, s));
     for (int q = 0; q < 2; ++q) NLB_CUDA(h, cudaStreamWaitEvent(h->pipe[q], h->ev_in, 0));
     int c = 0;
-    for (long long b0 = 0; b0 < B; b0 += chunk, ++c) {
-        const long long cnt = (B - b0 < chunk) ? (B - b0) : chunk;
+    for (long long b0 = 0; b0 < nb; b0 += chunk, ++c) {
+        const long long cnt = (nb - b0 < chunk) ? (nb - b0) : chunk;
         cudaStream_t st = h->pipe[c & 1];
+        nvtx_push("nlb H2D");
         for (int i = 0; i < 5; ++i) {
             if (a[i].st.staged && a[i].in)
-                NLB_CUDA(h, cudaMemcpy2DAsync((char*)a[i].st.dev + b0 * a[i].elem, (size_t)B * a[i].elem,
-                                              (const char*)a[i].st.user + b0 * a[i].elem, (size_t)B * a[i].elem,
+                NLB_CUDA(h, cudaMemcpy2DAsync((char*)a[i].st.dev + b0 * a[i].elem, (size_t)Bd * a[i].elem,
+                                              (const char*)a[i].st.user + b0 * a[i].elem, (size_t)Bh * a[i].elem,
                                               (size_t)cnt * a[i].elem, a[i].rows, cudaMemcpyHostToDevice, st));
         }
-        if ((rc = launch(b0, cnt, st))) return rc;
+        nvtx_pop();
+        nvtx_push("nlb solve kernel");
+        rc = launch(b0, cnt, st);
+        nvtx_pop();
+        if (rc) return rc;
+        nvtx_push("nlb D2H");
         for (int i = 0; i < 5; ++i) {
             if (a[i].st.staged && a[i].out)
-                NLB_CUDA(h, cudaMemcpy2DAsync((char*)a[i].st.user + b0 * a[i].elem, (size_t)B * a[i].elem,
-                                              (const char*)a[i].st.dev + b0 * a[i].elem, (size_t)B * a[i].elem,
+                NLB_CUDA(h, cudaMemcpy2DAsync((char*)a[i].st.user + b0 * a[i].elem, (size_t)Bh * a[i].elem,
+                                              (const char*)a[i].st.dev + b0 * a[i].elem, (size_t)Bd * a[i].elem,
                                               (size_t)cnt * a[i].elem, a[i].rows, cudaMemcpyDeviceToHost, st));
         }
+        nvtx_pop();
     }
     for (int q = 0; q < 2; ++q) {
         NLB_CUDA(h, cudaEventRecord(h->ev_out[q], h->pipe[q]));
         NLB_CUDA(h, cudaStreamWaitEvent(s, h->ev_out[q], 0));
     }
+    if (want_stats && (rc = shard_stats(s))) return rc;
     NLB_CUDA(h, cudaStreamSynchronize(s));
     return NLB_OK;
 }
@@ -723,6 +804,17 @@ int nlb_create(nlb_handle** handle, int device) {
         cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
         delete h;
         return NLB_ERR_CUDA;
+    }
+    // Work queues and workspaces are allocated stream-ordered per launch (cudaMallocAsync): keep freed blocks in the
+    // device's pool instead of returning them to the driver at every synchronisation (the default threshold of 0 makes
+    // each launch after a sync pay a fresh driver allocation: measured 10x on the host-buffer path of the Newton kernel).
+    {
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
     }
     *handle = h;
     return NLB_OK;
@@ -1158,3 +1250,132 @@ int nlb_measure_fp64_peak(nlb_handle* h, double* dfma_tflops, double* dadd_dmul_
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// one batch over several GPUs of one process
+// ---------------------------------------------------------------------------------------
+namespace {
+
+// NCCL is resolved at run time (libnccl.so.2: the copy torch has already loaded, or the system one), so that the
+// engine has no link-time dependency on it and single-GPU hosts never touch it.
+struct NcclApi {
+    typedef void* comm_t;
+    int (*CommInitAll)(comm_t*, int, const int*) = nullptr;
+    int (*CommDestroy)(comm_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+    NcclApi() {
+        void* lib = nullptr;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"})
+            if ((lib = dlopen(name, RTLD_LAZY | RTLD_GLOBAL))) break;
+        if (!lib) return;
+        CommInitAll = reinterpret_cast<decltype(CommInitAll)>(dlsym(lib, "ncclCommInitAll"));
+        CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+        GroupStart = reinterpret_cast<decltype(GroupStart)>(dlsym(lib, "ncclGroupStart"));
+        GroupEnd = reinterpret_cast<decltype(GroupEnd)>(dlsym(lib, "ncclGroupEnd"));
+        AllReduce = reinterpret_cast<decltype(AllReduce)>(dlsym(lib, "ncclAllReduce"));
+        GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+        ok = CommInitAll && CommDestroy && GroupStart && GroupEnd && AllReduce;
+    }
+};
+const NcclApi& nccl_api() { static const NcclApi api; return api; }
+constexpr int kNcclInt64 = 4, kNcclSum = 0, kNcclMax = 2;      // ncclDataType_t / ncclRedOp_t values (nccl.h)
+
+// communicators of one device list, created on first use and kept for the life of the process
+struct CommSet {
+    std::vector<int> devs;
+    std::vector<NcclApi::comm_t> comms;
+};
+std::mutex g_comm_mu;
+std::vector<CommSet*> g_comm_sets;
+
+int comms_for(const std::vector<int>& devs, CommSet** out, std::string* err) {
+    std::lock_guard<std::mutex> lock(g_comm_mu);
+    for (CommSet* cs : g_comm_sets)
+        if (cs->devs == devs) { *out = cs; return NLB_OK; }
+    const NcclApi& api = nccl_api();
+    if (!api.ok) { *err = "NCCL (libnccl.so.2) could not be loaded"; return NLB_ERR_UNSUPPORTED; }
+    CommSet* cs = new CommSet();
+    cs->devs = devs;
+    cs->comms.resize(devs.size());
+    const int r = api.CommInitAll(cs->comms.data(), (int)devs.size(), devs.data());
+    if (r != 0) {
+        *err = std::string("ncclCommInitAll: ") + (api.GetErrorString ? api.GetErrorString(r) : "error");
+        delete cs;
+        return NLB_ERR_CUDA;
+    }
+    g_comm_sets.push_back(cs);
+    *out = cs;
+    return NLB_OK;
+}
+
+}  // namespace
+
+extern "C" int nlb_solve_sharded(nlb_handle* const* handles, int ndev, int solver, const nlb_params* params, int fcn_id,
+                                 int64_t B, int m, int n, double* x, double* fvec, const double* sys, const double* shared,
+                                 nlb_iteration_behavior* ib, int32_t* status, int64_t* stats) {
+    if (!handles || ndev <= 0) return NLB_ERR_INVALID_ARGUMENT;
+    for (int d = 0; d < ndev; ++d)
+        if (!handles[d]) return NLB_ERR_INVALID_ARGUMENT;
+    nlb_handle* h0 = handles[0];
+    if (solver != NLB_SOLVER_LEAST_SQUARES && solver != NLB_SOLVER_NEWTON && solver != NLB_SOLVER_QUASI_NEWTON)
+        return set_err(h0, NLB_ERR_INVALID_ARGUMENT, "solver: NLB_SOLVER_LEAST_SQUARES / _NEWTON / _QUASI_NEWTON");
+    for (int d = 0; d < ndev; ++d)
+        for (int e = 0; e < d; ++e)
+            if (handles[d]->device == handles[e]->device)
+                return set_err(h0, NLB_ERR_INVALID_ARGUMENT, "one handle per device: two handles share a device");
+    // contiguous system ranges, sizes differing by at most one; one host thread per device
+    std::vector<int> rc(ndev, NLB_OK);
+    std::vector<std::thread> workers;
+    const int64_t base = B / ndev, rem = B % ndev;
+    for (int d = 0; d < ndev; ++d) {
+        const int64_t lo = d * base + (d < rem ? d : rem);
+        const int64_t cnt = base + (d < rem ? 1 : 0);
+        workers.emplace_back([=, &rc] {
+            rc[d] = solve_batch(handles[d], solver, params, fcn_id, B, m, n, x, fvec, sys, shared, ib, status, nullptr,
+                                nullptr, lo, cnt, stats != nullptr);
+        });
+    }
+    for (std::thread& t : workers) t.join();
+    for (int d = 0; d < ndev; ++d)
+        if (rc[d] != NLB_OK) {
+            if (d != 0) set_err(h0, rc[d], handles[d]->last_error.c_str());
+            return rc[d];
+        }
+    if (!stats) return NLB_OK;
+    // the one collective of the path: convergence statistics, SUM (MAX for max_iter), NCCL over NVLink
+    if (ndev > 1) {
+        std::vector<int> devs(ndev);
+        for (int d = 0; d < ndev; ++d) devs[d] = handles[d]->device;
+        CommSet* cs = nullptr;
+        std::string err;
+        const int r = comms_for(devs, &cs, &err);
+        if (r != NLB_OK) return set_err(h0, r, err.c_str());
+        const NcclApi& api = nccl_api();
+        int nr = api.GroupStart();
+        for (int d = 0; d < ndev && nr == 0; ++d) {
+            int64_t* v = handles[d]->dstats;
+            nr = api.AllReduce(v, v, NLB_STAT_MAX_ITER, kNcclInt64, kNcclSum, cs->comms[d], handles[d]->stream);
+            if (nr == 0)
+                nr = api.AllReduce(v + NLB_STAT_MAX_ITER, v + NLB_STAT_MAX_ITER, 1, kNcclInt64, kNcclMax, cs->comms[d],
+                                   handles[d]->stream);
+        }
+        const int ne = api.GroupEnd();
+        if (nr == 0) nr = ne;
+        if (nr != 0) return set_err(h0, NLB_ERR_CUDA, api.GetErrorString ? api.GetErrorString(nr) : "NCCL error");
+    }
+    {
+        DeviceGuard guard(h0->device);
+        if (guard.err != cudaSuccess) return set_err(h0, NLB_ERR_NO_DEVICE, "cudaSetDevice", guard.err);
+        NLB_CUDA(h0, cudaMemcpyAsync(stats, h0->dstats, sizeof(int64_t) * NLB_STAT_COUNT, cudaMemcpyDeviceToHost, h0->stream));
+        NLB_CUDA(h0, cudaStreamSynchronize(h0->stream));
+    }
+    for (int d = 1; d < ndev; ++d) {
+        DeviceGuard guard(handles[d]->device);
+        cudaStreamSynchronize(handles[d]->stream);
+    }
+    return NLB_OK;
+}

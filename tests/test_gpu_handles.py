@@ -62,3 +62,54 @@ def test_two_handles_one_process(engine):
         assert torch.cuda.current_device() == 0      # the C ABI restores the caller's device
     finally:
         second.close()
+
+
+def test_sharded_solve_over_all_devices(engine, oracle):
+    """nlb_solve_sharded: one host batch over every GPU of the box (one handle per device, one host thread each, NCCL
+    all-reduce of the statistics when there is more than one) gives the bits of the single-device solve."""
+    import torch
+
+    import nonlin_b200 as nb
+    from nonlin_b200 import workloads as W
+
+    ndev = torch.cuda.device_count()
+    engines = [engine] + [nb.Engine(d) for d in range(1, ndev)]
+    try:
+        for name, B in (("C2", 10007), ("C1", 4099), ("C3", 5000)):
+            w = W.WORKLOADS[name](B)
+            ref = _solve(nb, engine, w)
+            obj = nb.vecfcn_helper()
+            obj.set_fcn(w["fcn"], w["m"], w["n"])
+            s = {"least_squares": nb.least_squares_solver, "quasi_newton": nb.quasi_newton_solver,
+                 "newton": nb.newton_solver}[w["solver"]]()
+            for k, v in w["settings"].items():
+                getattr(s, k)(v)
+            x = w["x0"].copy()
+            f = np.zeros((w["m"], B))
+            ib = nb.iteration_behavior(B)
+            st, stats = s.solve_sharded(engines, obj, x, f, ib, args=w["args"])
+            for u, v in zip(ref, (x, f, ib, st)):
+                assert np.array_equal(u, v)
+            assert stats["systems"] == B and stats["converged"] == int((st == 0).sum())
+            assert stats["sum_iter"] == int(ib["iter_count"].sum()) and stats["max_iter"] == int(ib["iter_count"].max())
+            # outputs that are not asked for are not produced
+            x2 = w["x0"].copy()
+            st2, none = s.solve_sharded(engines, obj, x2, None, None, args=w["args"], want_stats=False)
+            assert none is None and np.array_equal(x2, x) and np.array_equal(st2, st)
+    finally:
+        for e in engines[1:]:
+            e.close()
+
+
+def test_optional_outputs_single_device(engine):
+    import nonlin_b200 as nb
+    from nonlin_b200 import workloads as W
+
+    w = W.WORKLOADS["C2"](70001)
+    ref = _solve(nb, engine, w)
+    obj = nb.vecfcn_helper()
+    obj.set_fcn(w["fcn"], w["m"], w["n"])
+    s = nb.quasi_newton_solver(engine=engine)
+    x = w["x0"].copy()
+    st = s.solve(obj, x, want_fvec=False)
+    assert np.array_equal(x, ref[0]) and np.array_equal(st, ref[3])

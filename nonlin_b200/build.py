@@ -39,6 +39,24 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+LIB_FAST = os.path.join(HERE, "libnonlin_b200_fast.so")
+
+
+def build_fast(force=False):
+    """The same sources WITH FMA contraction (nvcc's default): not bit-compatible with the reference's arithmetic, kept as
+    a separate library that is only ever loaded explicitly (NLB_LIB=...; scripts/fast_build_stats.py measures how far its
+    results move: x / f agreement and equality of the iteration counts against the CPU oracle)."""
+    if not force and os.path.exists(LIB_FAST) and os.path.getmtime(LIB_FAST) >= max(
+            os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC)):
+        return LIB_FAST
+    flags = [f for f in NVCC_FLAGS if f != "-fmad=false"]
+    cmd = [_nvcc()] + flags + ["-o", LIB_FAST] + [os.path.join(CSRC, s) for s in SOURCES]
+    if os.path.exists("/usr/bin/g++"):
+        cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
+    subprocess.check_call(cmd)
+    return LIB_FAST
+
+
 def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
@@ -54,4 +72,7 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--fast" in sys.argv:
+        print(build_fast(force="--force" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

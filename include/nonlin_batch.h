@@ -125,6 +125,25 @@ int nlb_vecfcn_lookup(const char* name);            /* id or -1 */
 const char* nlb_vecfcn_name(int fcn_id);            /* NULL if unknown */
 int nlb_vecfcn_info(int fcn_id, int* m, int* n, int* sys_len, int* shared_len, int* has_jacobian);
 
+/* Residuals compiled outside the engine (plug-ins): vecfcn_helper%set_fcn takes any procedure at run time
+ * (src/nonlin_multi_eqn_mult_var.f90:126-140); a __device__ function cannot cross a library boundary, so a new residual
+ * is a small library built from nonlin_b200/csrc/nlb_plugin.cuh (see there) that hands the engine host-side launchers
+ * of the engine's own kernel templates instantiated for it.  No rebuild of the engine is involved.
+ *   nlb_load_plugin      dlopen the library and let it register its residuals; returns how many, or -1
+ *   nlb_register_vecfcn  what the plug-in calls for each of them; returns the new id (>= the built-in count) or -1
+ * Registered residuals resolve through nlb_vecfcn_lookup / _name / _info like the built-in ones and are served by the
+ * least-squares, Newton, quasi-Newton, evaluation and Jacobian entry points (thread-per-system kernels; fixed m, n). */
+typedef int (*nlb_user_solve_fn)(int solver, const struct nlb_params* params, int64_t nsys, int64_t B, double* x,
+                                 double* fvec, const double* sys, const double* shared,
+                                 struct nlb_iteration_behavior* ib, int32_t* status, void* stream);
+typedef int (*nlb_user_eval_fn)(int what /* 0 residual, 1 Jacobian */, int analytic, int64_t B, const double* x, double* out,
+                                const double* sys, const double* shared, void* stream);
+typedef int (*nlb_register_vecfcn_fn)(const char* name, int m, int n, int sys_len, int shared_len, int has_jacobian,
+                                      nlb_user_solve_fn solve, nlb_user_eval_fn eval);
+int nlb_register_vecfcn(const char* name, int m, int n, int sys_len, int shared_len, int has_jacobian,
+                        nlb_user_solve_fn solve, nlb_user_eval_fn eval);
+int nlb_load_plugin(const char* path);
+
 /* least_squares_solver%solve  (lss_solve, src/nonlin_least_squares.f90:118-391) over B systems.
  * x in/out, fvec out, ib / status out (fvec, ib and status may each be NULL: an output that is not asked for is not
  * copied back - for host buffers the call is PCIe-bound and x + status are 20 of the 64 bytes per 2x2 system). stream: cudaStream_t, or NULL for the

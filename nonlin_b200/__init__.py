@@ -39,6 +39,7 @@ from .api import (  # noqa: F401
     least_squares_solver,
     line_search,
     line_search_solver,
+    load_plugin,
     newton_1var_solver,
     newton_solver,
     polynomial,

@@ -45,7 +45,7 @@ EXPORTS = [
     "nlb_measure_fp64_latency", "nlb_constrained_options_default", "nlb_constrained_least_squares_solve_batch",
     "nlb_polynomial_fit_batch", "nlb_polynomial_evaluate_batch",
     "nlb_params_1var_default", "nlb_fcn1var_count", "nlb_fcn1var_lookup", "nlb_fcn1var_name", "nlb_fcn1var_info",
-    "nlb_brent_solve_batch", "nlb_newton_1var_solve_batch", "nlb_solve_sharded",
+    "nlb_brent_solve_batch", "nlb_newton_1var_solve_batch", "nlb_solve_sharded", "nlb_register_vecfcn", "nlb_load_plugin",
 ]
 
 NLB_SOLVER_LEAST_SQUARES, NLB_SOLVER_NEWTON, NLB_SOLVER_QUASI_NEWTON = 0, 1, 2
@@ -141,6 +141,7 @@ def load():
     lib.nlb_vecfcn_eval_batch.argtypes = [vp, i32, i64, i32, i32, vp, vp, vp, vp, vp]
     lib.nlb_jacobian_batch.argtypes = [vp, C.POINTER(nlb_params), i32, i64, i32, i32, vp, vp, vp, vp, vp]
     lib.nlb_reduce_stats.argtypes = [vp, i64, vp, vp, vp, vp]
+    lib.nlb_load_plugin.argtypes = [C.c_char_p]
     lib.nlb_solve_sharded.argtypes = [C.POINTER(vp), i32, i32, C.POINTER(nlb_params), i32, i64, i32, i32, vp, vp, vp, vp, vp,
                                       vp, vp]
     lib.nlb_measure_fp64_peak.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl)]

@@ -96,6 +96,15 @@ class Engine:
 _default_engines = {}
 
 
+def load_plugin(path):
+    """Load a residual plug-in library (built from nonlin_b200/csrc/nlb_plugin.cuh; see examples/plugin/) and register the
+    residuals it carries - the batch analogue of handing vecfcn_helper%set_fcn a new procedure.  Returns how many."""
+    n = _LIB.nlb_load_plugin(str(path).encode())
+    if n < 0:
+        raise NonlinError(_lib.NLB_ERR_INVALID_ARGUMENT, "cannot load residual plug-in %s" % path)
+    return n
+
+
 def default_engine(device=0):
     e = _default_engines.get(device)
     if e is None:

@@ -10,6 +10,7 @@
 #include <string>
 
 #include <cstdlib>
+#include <deque>
 #include <dlfcn.h>
 #include <thread>
 #include <vector>
@@ -20,8 +21,7 @@
 #include "quad_lm.cuh"
 #include "scalar_solvers.cuh"
 #include "tps_cls.cuh"
-#include "tps_lm.cuh"
-#include "tps_newton_broyden.cuh"
+#include "tps_kernels.cuh"
 
 using namespace nlb;
 
@@ -50,7 +50,6 @@ struct nlb_handle {
 
 namespace {
 
-enum Solver { SOLVER_LM = 0, SOLVER_NEWTON = 1, SOLVER_BROYDEN = 2, SOLVER_CLS = 3 };
 
 int set_err(nlb_handle* h, int code, const char* what, cudaError_t ce = cudaSuccess) {
     if (h) {
@@ -136,73 +135,6 @@ int stage_out(nlb_handle* h, const Staged& a, cudaStream_t s) {
     return NLB_OK;
 }
 
-DevParams to_dev(const nlb_params* p) {
-    DevParams d;
-    d.max_fcn_evals = p->max_fcn_evals;
-    d.fcn_tol = p->fcn_tol;
-    d.var_tol = p->var_tol;
-    d.grad_tol = p->grad_tol;
-    d.lm_factor = p->lm_factor;
-    d.jacobian_interval = p->jacobian_interval;
-    d.use_line_search = p->use_line_search;
-    d.ls_max_fcn_evals = p->ls_max_fcn_evals;
-    d.ls_alpha = p->ls_alpha;
-    d.ls_factor = p->ls_factor;
-    d.use_analytic_jacobian = p->use_analytic_jacobian;
-    d.max_iter_guard = p->max_iter_guard;
-    return d;
-}
-
-// ---------------------------------------------------------------------------------------
-// thread-per-system kernels
-// ---------------------------------------------------------------------------------------
-#ifndef NLB_TPS_BLOCK
-#define NLB_TPS_BLOCK 128
-#endif
-constexpr int TPS_BLOCK = NLB_TPS_BLOCK;
-// Minimum resident CTAs per SM asked of ptxas.  Measured on B200 (launch-bounds sweep): capping the
-// 2x2 Broyden kernel at 80 registers (6 CTAs/SM) is 11 % faster than 110 registers (4 CTAs/SM); LM is best at
-// 3 CTAs/SM (160 registers); Newton does not gain from a cap.
-template <int SOLVER>
-constexpr int tps_min_blocks() {
-    return SOLVER == 2 ? 6 : (SOLVER == 0 ? 3 : 1);
-}
-
-template <class F, int SOLVER>
-__global__ void __launch_bounds__(TPS_BLOCK, tps_min_blocks<SOLVER>())
-tps_solve_kernel(DevParams p, long long nsys, long long B, double* __restrict__ x, double* __restrict__ fvec,
-                 const double* __restrict__ sys, const double* __restrict__ shared,
-                 nlb_iteration_behavior* __restrict__ ib, int32_t* __restrict__ status) {
-    // nsys systems starting at the (pre-offset) pointers; B is the SoA stride of the whole batch
-    constexpr int M = F::M, N = F::N;
-    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (b >= nsys) return;
-    double xl[N], fl[M];
-#pragma unroll
-    for (int j = 0; j < N; ++j) xl[j] = x[j * B + b];
-    SysCtx c{sys ? sys + b : nullptr, shared, B, M, N};
-    SolveStats st;
-    if constexpr (SOLVER == SOLVER_LM) tps_lm_solve<F>(p, c, xl, fl, st);
-    else if constexpr (SOLVER == SOLVER_NEWTON) tps_newton_solve<F>(p, c, xl, fl, st);
-    else tps_broyden_solve<F>(p, c, xl, fl, st);
-#pragma unroll
-    for (int j = 0; j < N; ++j) x[j * B + b] = xl[j];
-#pragma unroll(M <= 8 ? M : 1)
-    for (int i = 0; i < M; ++i) fvec[i * B + b] = fl[i];
-    if (ib) {
-        nlb_iteration_behavior o;
-        o.iter_count = st.iter;
-        o.fcn_count = st.nfev;
-        o.jacobian_count = st.njac;
-        o.gradient_count = 0;
-        o.converge_on_fcn = st.cf;
-        o.converge_on_chng = st.cx;
-        o.converge_on_zero_diff = st.cg;
-        ib[b] = o;
-    }
-    if (status) status[b] = st.status;
-}
-
 // Levenberg-Marquardt with the m x n Jacobian in shared memory ([element][thread] tile, 8 M N bytes per thread): for
 // residuals whose Jacobian does not fit the register file (21 x 4: 86 KB per CTA, two CTAs per SM).  The two m-vectors
 // stay in local memory, where they fit L1 next to the tile.  Experimental: slower than the local-memory kernel on
@@ -258,39 +190,6 @@ tps_newton_refill_kernel(DevParams p, long long nsys, long long B, unsigned long
                          double* __restrict__ fvec, const double* __restrict__ sys, const double* __restrict__ shared,
                          nlb_iteration_behavior* __restrict__ ib, int32_t* __restrict__ status) {
     tps_newton_refill<F>(p, nsys, B, cursor, x, fvec, sys, shared, ib, status);
-}
-
-template <class F>
-__global__ void __launch_bounds__(TPS_BLOCK)
-tps_eval_kernel(long long B, const double* __restrict__ x, double* __restrict__ fvec,
-                const double* __restrict__ sys, const double* __restrict__ shared) {
-    constexpr int M = F::M, N = F::N;
-    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    double xl[N], fl[M];
-#pragma unroll
-    for (int j = 0; j < N; ++j) xl[j] = x[j * B + b];
-    SysCtx c{sys ? sys + b : nullptr, shared, B, M, N};
-    F::eval(xl, fl, c);
-#pragma unroll(M <= 8 ? M : 1)
-    for (int i = 0; i < M; ++i) fvec[i * B + b] = fl[i];
-}
-
-template <class F>
-__global__ void __launch_bounds__(TPS_BLOCK)
-tps_jacobian_kernel(int analytic, long long B, const double* __restrict__ x, double* __restrict__ jac,
-                    const double* __restrict__ sys, const double* __restrict__ shared) {
-    constexpr int M = F::M, N = F::N;
-    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    double xl[N], fl[M], wrk[M], jl[M * N];
-#pragma unroll
-    for (int j = 0; j < N; ++j) xl[j] = x[j * B + b];
-    SysCtx c{sys ? sys + b : nullptr, shared, B, M, N};
-    F::eval(xl, fl, c);                      // fv not supplied: evaluate f(x) first (multi_eqn:257-259)
-    fd_jacobian<F>(xl, jl, fl, wrk, c, analytic != 0);
-#pragma unroll(M * N <= 16 ? M * N : 1)
-    for (int e = 0; e < M * N; ++e) jac[e * B + b] = jl[e];
 }
 
 // ---------------------------------------------------------------------------------------
@@ -594,9 +493,37 @@ int solve_1var_batch(nlb_handle* h, int solver, const nlb_params_1var* params, i
     return NLB_OK;
 }
 
+// residuals registered at run time by plug-ins (nlb_plugin.cuh): ids FCN_COUNT, FCN_COUNT + 1, ...
+struct UserFcn {
+    std::string name;
+    int m, n, sys_len, shared_len, has_jac;
+    nlb_user_solve_fn solve;
+    nlb_user_eval_fn eval;
+};
+std::mutex g_user_mu;
+std::deque<UserFcn> g_user;                      // deque: entries never move once registered
+
+int fcn_total() {
+    std::lock_guard<std::mutex> lock(g_user_mu);
+    return FCN_COUNT + (int)g_user.size();
+}
+const UserFcn* user_fcn(int fcn_id) {
+    std::lock_guard<std::mutex> lock(g_user_mu);
+    const int k = fcn_id - FCN_COUNT;
+    return (k >= 0 && k < (int)g_user.size()) ? &g_user[k] : nullptr;
+}
+bool fcn_info(int fcn_id, FcnInfo* fi) {
+    if (fcn_id >= 0 && fcn_id < FCN_COUNT) { *fi = fcn_table()[fcn_id]; return true; }
+    if (const UserFcn* u = user_fcn(fcn_id)) {
+        *fi = FcnInfo{u->name.c_str(), u->m, u->n, u->sys_len, u->shared_len, u->has_jac};
+        return true;
+    }
+    return false;
+}
+
 int check_sizes(nlb_handle* h, int fcn_id, int* m, int* n, int* sys_len, int* shared_len) {
-    if (fcn_id < 0 || fcn_id >= FCN_COUNT) return set_err(h, NLB_ERR_UNKNOWN_FCN, "unknown residual id");
-    const FcnInfo& fi = fcn_table()[fcn_id];
+    FcnInfo fi;
+    if (!fcn_info(fcn_id, &fi)) return set_err(h, NLB_ERR_UNKNOWN_FCN, "unknown residual id");
     if (fi.m != 0) { if (*m != 0 && *m != fi.m) return set_err(h, NLB_ERR_SIZE, "m does not match the residual"); *m = fi.m; }
     if (fi.n != 0) { if (*n != 0 && *n != fi.n) return set_err(h, NLB_ERR_SIZE, "n does not match the residual"); *n = fi.n; }
     if (fcn_id == FCN_EXT_ROSENBROCK) {
@@ -681,7 +608,9 @@ int solve_batch(nlb_handle* h, int solver, const nlb_params* params, int fcn_id,
     any_staged = any_staged || ash.staged;
 
     const DevParams p = to_dev(params);
-    const FcnInfo& fi = fcn_table()[fcn_id];
+    FcnInfo fi;
+    fcn_info(fcn_id, &fi);
+    const UserFcn* ufcn = user_fcn(fcn_id);
     auto launch = [&](long long b0, long long cnt, cudaStream_t st) -> int {
         double* dx = (double*)a[0].st.dev + b0;
         double* df = (double*)a[1].st.dev + b0;
@@ -690,7 +619,13 @@ int solve_batch(nlb_handle* h, int solver, const nlb_params* params, int fcn_id,
         int32_t* dst = a[4].st.dev ? (int32_t*)a[4].st.dev + b0 : nullptr;
         const double* dsh = (const double*)ash.dev;
         int r;
-        if (solver == SOLVER_CLS) {
+        if (ufcn) {
+            if (solver == SOLVER_CLS) return set_err(h, NLB_ERR_UNSUPPORTED, "constrained least squares: built-in residuals only");
+            r = ufcn->solve(solver, params, cnt, Bd, dx, df, ds, dsh, dib, dst, (void*)st);
+            ++h->launches;
+            if (r == NLB_ERR_CUDA) return set_err(h, r, "plug-in kernel launch", cudaGetLastError());
+            if (r != NLB_OK) return set_err(h, r, "the plug-in residual does not serve this solver");
+        } else if (solver == SOLVER_CLS) {
             r = (fi.m != 0 && fi.n != 0)
                     ? dispatch_cls(h, fcn_id, p, *cls, cnt, Bd, dx, df, ds, dsh, dib, dst, st)
                     : set_err(h, NLB_ERR_UNSUPPORTED, "constrained least squares: fixed-size residuals only");
@@ -857,23 +792,46 @@ void nlb_params_default(nlb_params* p) {
     p->max_iter_guard = 100000;
 }
 
-int nlb_vecfcn_count(void) { return FCN_COUNT; }
+int nlb_vecfcn_count(void) { return fcn_total(); }
 
 int nlb_vecfcn_lookup(const char* name) {
     if (!name) return -1;
     for (int i = 0; i < FCN_COUNT; ++i)
         if (std::strcmp(fcn_table()[i].name, name) == 0) return i;
+    std::lock_guard<std::mutex> lock(g_user_mu);
+    for (size_t k = 0; k < g_user.size(); ++k)
+        if (g_user[k].name == name) return FCN_COUNT + (int)k;
     return -1;
 }
 
 const char* nlb_vecfcn_name(int fcn_id) {
-    if (fcn_id < 0 || fcn_id >= FCN_COUNT) return nullptr;
-    return fcn_table()[fcn_id].name;
+    if (fcn_id >= 0 && fcn_id < FCN_COUNT) return fcn_table()[fcn_id].name;
+    const UserFcn* u = user_fcn(fcn_id);
+    return u ? u->name.c_str() : nullptr;
+}
+
+int nlb_register_vecfcn(const char* name, int m, int n, int sys_len, int shared_len, int has_jacobian,
+                        nlb_user_solve_fn solve, nlb_user_eval_fn eval) {
+    if (!name || !*name || m <= 0 || n <= 0 || sys_len < 0 || shared_len < 0 || !solve) return -1;
+    if (nlb_vecfcn_lookup(name) >= 0) return -1;                 // names are unique
+    std::lock_guard<std::mutex> lock(g_user_mu);
+    g_user.push_back(UserFcn{name, m, n, sys_len, shared_len, has_jacobian ? 1 : 0, solve, eval});
+    return FCN_COUNT + (int)g_user.size() - 1;
+}
+
+int nlb_load_plugin(const char* path) {
+    if (!path) return -1;
+    void* lib = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!lib) return -1;
+    typedef int (*entry_t)(nlb_register_vecfcn_fn);
+    entry_t entry = reinterpret_cast<entry_t>(dlsym(lib, "nlb_plugin_register"));
+    if (!entry) { dlclose(lib); return -1; }
+    return entry(&nlb_register_vecfcn);                           // the library stays loaded: its kernels are in use
 }
 
 int nlb_vecfcn_info(int fcn_id, int* m, int* n, int* sys_len, int* shared_len, int* has_jacobian) {
-    if (fcn_id < 0 || fcn_id >= FCN_COUNT) return NLB_ERR_UNKNOWN_FCN;
-    const FcnInfo& fi = fcn_table()[fcn_id];
+    FcnInfo fi;
+    if (!fcn_info(fcn_id, &fi)) return NLB_ERR_UNKNOWN_FCN;
     if (m) *m = fi.m;
     if (n) *n = fi.n;
     if (sys_len) *sys_len = fi.sys_len;
@@ -914,8 +872,8 @@ int nlb_constrained_least_squares_solve_batch(nlb_handle* h, const nlb_params* p
                                               nlb_iteration_behavior* ib, int32_t* status, void* stream) {
     if (!h) return NLB_ERR_INVALID_ARGUMENT;
     if (!options) return set_err(h, NLB_ERR_INVALID_ARGUMENT, "null options");
-    if (fcn_id < 0 || fcn_id >= FCN_COUNT) return set_err(h, NLB_ERR_UNKNOWN_FCN, "unknown residual id");
-    const FcnInfo& fi = fcn_table()[fcn_id];
+    FcnInfo fi;
+    if (!fcn_info(fcn_id, &fi)) return set_err(h, NLB_ERR_UNKNOWN_FCN, "unknown residual id");
     const int nv = fi.n != 0 ? fi.n : n;
     if (nv <= 0 || nv > CLS_MAX_N) return set_err(h, NLB_ERR_UNSUPPORTED, "constrained least squares: n <= 8");
     DevCls o;
@@ -1115,8 +1073,14 @@ int nlb_vecfcn_eval_batch(nlb_handle* h, int fcn_id, int64_t B, int m, int n, co
         NLB_FIXED_FCNS(X)
 #undef X
         default:
-            rc = launch_coop_eval(fcn_id, B, m, n, (const double*)ax.dev, (double*)af.dev, (const double*)as.dev,
-                                  (const double*)ash.dev, s);
+            if (const UserFcn* u = user_fcn(fcn_id)) {
+                rc = u->eval ? u->eval(0, 0, B, (const double*)ax.dev, (double*)af.dev, (const double*)as.dev,
+                                       (const double*)ash.dev, (void*)s)
+                             : NLB_ERR_UNSUPPORTED;
+            } else {
+                rc = launch_coop_eval(fcn_id, B, m, n, (const double*)ax.dev, (double*)af.dev, (const double*)as.dev,
+                                      (const double*)ash.dev, s);
+            }
             if (rc) return set_err(h, rc, "no evaluation kernel for this residual");
     }
     ++h->launches;
@@ -1153,8 +1117,14 @@ int nlb_jacobian_batch(nlb_handle* h, const nlb_params* params, int fcn_id, int6
         NLB_FIXED_FCNS(X)
 #undef X
         default:
-            rc = launch_coop_jacobian(fcn_id, B, m, n, (const double*)ax.dev, (double*)aj.dev, (const double*)as.dev,
-                                      (const double*)ash.dev, s);
+            if (const UserFcn* u = user_fcn(fcn_id)) {
+                rc = u->eval ? u->eval(1, params->use_analytic_jacobian, B, (const double*)ax.dev, (double*)aj.dev,
+                                       (const double*)as.dev, (const double*)ash.dev, (void*)s)
+                             : NLB_ERR_UNSUPPORTED;
+            } else {
+                rc = launch_coop_jacobian(fcn_id, B, m, n, (const double*)ax.dev, (double*)aj.dev, (const double*)as.dev,
+                                          (const double*)ash.dev, s);
+            }
             if (rc) return set_err(h, rc, "no Jacobian kernel for this residual");
     }
     ++h->launches;

@@ -109,6 +109,30 @@ class Oracle:
         lib.nlo_polyval_batch.restype = C.c_int
         lib.nlo_cls_solve_batch.restype = C.c_int
 
+    # -- residuals supplied by a test as Python callbacks (checker for plug-in residuals) ---
+    CALLBACK = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                           C.c_int, C.c_int)
+    _callbacks = {}
+
+    def register_callback(self, name, m, n, fcn, sys_len=0, shared_len=0):
+        """fcn(x, sys, shared) -> sequence of m floats, evaluated with Python floats (IEEE doubles, no contraction).
+        Solve callback residuals with nthreads=1."""
+        def tramp(xp, fp, sp, hp, mm, nn):
+            x = [xp[j] for j in range(nn)]
+            sysv = [sp[k] for k in range(sys_len)] if sys_len else None
+            shv = [hp[k] for k in range(shared_len)] if shared_len else None
+            out = fcn(x, sysv, shv)
+            for i in range(mm):
+                fp[i] = out[i]
+        cb = Oracle.CALLBACK(tramp)
+        self.lib.nlo_register_callback.restype = C.c_int
+        self.lib.nlo_register_callback.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, Oracle.CALLBACK]
+        fid = self.lib.nlo_register_callback(name.encode(), m, n, sys_len, shared_len, cb)
+        if fid < 0:
+            raise RuntimeError("nlo_register_callback failed")
+        Oracle._callbacks[(id(self.lib), name)] = cb          # keep the trampoline alive
+        return fid
+
     # -- registry -----------------------------------------------------------------------
     def fcn_id(self, name):
         i = self.lib.nlo_fcn_lookup(name.encode())

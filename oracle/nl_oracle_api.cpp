@@ -85,6 +85,11 @@ int nlo_fcn_info(int id, int* m, int* n, int* sys_len, int* shared_len, int* has
 
 void nlo_params_default(Params* p) { params_default(p); }
 
+// a residual supplied by the test as a C callback (checker for plug-in residuals); returns its id or -1
+int nlo_register_callback(const char* name, int m, int n, int sys_len, int shared_len, callback_t fcn) {
+    return nl_register_callback(name, m, n, sys_len, shared_len, fcn);
+}
+
 double nlo_soft_exp(double x) { return soft_exp_d(x); }
 double nlo_norm2(const double* v, int n) { return dval(f_norm2(R(v), n)); }
 double nlo_dnrm2(const double* v, int n) { return dval(la_dnrm2(n, R(v), 1)); }

@@ -165,7 +165,40 @@ static const Problem g_problems[NL_FCN_COUNT] = {
     {NL_FCN_EXP_DECAY_4, "exp_decay_4", 0, 4, -1, -1, exp_decay_4, nullptr},
 };
 
+// ---- callback residuals (one trampoline per slot: vecfcn_t carries no user data) ---------------------------------
+static callback_t g_cb[NL_MAX_CALLBACKS] = {nullptr, nullptr, nullptr, nullptr};
+static Problem g_cb_problem[NL_MAX_CALLBACKS];
+static char g_cb_name[NL_MAX_CALLBACKS][64];
+static int g_cb_count = 0;
+
+template <int K>
+static void cb_trampoline(const real* x, real* f, const FcnCtx* c) {
+    double xd[64], fd[64];
+    for (int j = 0; j < c->n; ++j) xd[j] = dval(x[j]);
+    const Problem& p = g_cb_problem[K];
+    double sd[64], hd[64];
+    const int ns = p.sys_len < 0 ? c->m : p.sys_len, nh = p.shared_len < 0 ? c->m : p.shared_len;
+    for (int k = 0; k < ns && c->sys; ++k) sd[k] = dval(c->sys[k]);
+    for (int k = 0; k < nh && c->shared; ++k) hd[k] = dval(c->shared[k]);
+    g_cb[K](xd, fd, c->sys ? sd : nullptr, c->shared ? hd : nullptr, c->m, c->n);
+    for (int i = 0; i < c->m; ++i) f[i] = real(fd[i]);
+}
+
+int nl_register_callback(const char* name, int m, int n, int sys_len, int shared_len, callback_t fcn) {
+    static const vecfcn_t tramp[NL_MAX_CALLBACKS] = {cb_trampoline<0>, cb_trampoline<1>, cb_trampoline<2>, cb_trampoline<3>};
+    if (!name || !fcn || m <= 0 || n <= 0 || m > 64 || n > 64 || sys_len > 64 || shared_len > 64) return -1;
+    for (int k = 0; k < g_cb_count; ++k)
+        if (std::strcmp(g_cb_name[k], name) == 0) { g_cb[k] = fcn; return NL_FCN_COUNT + k; }   // re-registration
+    if (g_cb_count >= NL_MAX_CALLBACKS) return -1;
+    const int k = g_cb_count++;
+    std::strncpy(g_cb_name[k], name, sizeof(g_cb_name[k]) - 1);
+    g_cb[k] = fcn;
+    g_cb_problem[k] = Problem{NL_FCN_COUNT + k, g_cb_name[k], m, n, sys_len, shared_len, tramp[k], nullptr};
+    return NL_FCN_COUNT + k;
+}
+
 const Problem* nl_problem(int id) {
+    if (id >= NL_FCN_COUNT && id < NL_FCN_COUNT + g_cb_count) return &g_cb_problem[id - NL_FCN_COUNT];
     if (id < 0 || id >= NL_FCN_COUNT) return nullptr;
     return &g_problems[id];
 }
@@ -173,6 +206,8 @@ const Problem* nl_problem(int id) {
 const Problem* nl_problem_by_name(const char* name) {
     for (int i = 0; i < NL_FCN_COUNT; ++i)
         if (std::strcmp(g_problems[i].name, name) == 0) return &g_problems[i];
+    for (int k = 0; k < g_cb_count; ++k)
+        if (std::strcmp(g_cb_name[k], name) == 0) return &g_cb_problem[k];
     return nullptr;
 }
 

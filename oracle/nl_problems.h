@@ -49,6 +49,12 @@ enum {
     NL_FCN_COUNT = 12
 };
 
+// Residuals supplied by the TEST as C callbacks (ids NL_FCN_COUNT ... NL_FCN_COUNT + NL_MAX_CALLBACKS - 1): the checker for
+// residuals that reach the engine as plug-ins (nonlin_b200/csrc/nlb_plugin.cuh).  The callback works on plain doubles.
+typedef void (*callback_t)(const double* x, double* f, const double* sys, const double* shared, int m, int n);
+enum { NL_MAX_CALLBACKS = 4 };
+int nl_register_callback(const char* name, int m, int n, int sys_len, int shared_len, callback_t fcn);   // id or -1
+
 const Problem* nl_problem(int id);
 const Problem* nl_problem_by_name(const char* name);
 

@@ -102,9 +102,9 @@ def test_registry_matches_oracle_table(oracle):
     from nonlin_b200 import _lib
 
     lib = _lib.load()
-    n = lib.nlb_vecfcn_count()
-    assert n == 12
-    for fid in range(n):
+    BUILTIN = 12                          # residuals compiled into the engine; plug-ins loaded by other tests come after
+    assert lib.nlb_vecfcn_count() >= BUILTIN
+    for fid in range(BUILTIN):
         name = lib.nlb_vecfcn_name(fid).decode()
         assert lib.nlb_vecfcn_lookup(name.encode()) == fid
         assert oracle.fcn_id(name) == fid

@@ -166,6 +166,22 @@ module nonlin_batch
             integer(c_int64_t), value :: b
             type(c_ptr), value :: ib, status, stats, stream
         end function
+        !> One batch over several GPUs of this process (include/nonlin_batch.h: nlb_solve_sharded).  handles = array of
+        !> engine handles (one per device); solver = 0 least squares, 1 Newton, 2 quasi-Newton; all data in host memory.
+        integer(c_int) function nlb_solve_sharded(handles, ndev, solver, params, fcn_id, b, m, n, x, fvec, sys, shared, &
+                ib, status, stats) bind(C, name = "nlb_solve_sharded")
+            import :: c_ptr, c_int, c_int64_t, nlb_params
+            type(c_ptr), intent(in) :: handles(*)
+            integer(c_int), value :: ndev, solver, fcn_id, m, n
+            type(nlb_params), intent(in) :: params
+            integer(c_int64_t), value :: b
+            type(c_ptr), value :: x, fvec, sys, shared, ib, status, stats
+        end function
+        !> Residual plug-ins (nonlin_b200/csrc/nlb_plugin.cuh): load a library of residuals compiled outside the engine.
+        integer(c_int) function nlb_load_plugin(path) bind(C, name = "nlb_load_plugin")
+            import :: c_int, c_char
+            character(kind = c_char), intent(in) :: path(*)
+        end function
     end interface
 
     !> One engine handle per GPU (stream + staging workspace).
@@ -213,6 +229,10 @@ module nonlin_batch
         procedure, public :: set_fcn_tolerance => bes_set_fcn_tol
         procedure, public :: set_var_tolerance => bes_set_var_tol
         procedure, public :: set_gradient_tolerance => bes_set_grad_tol
+        procedure, public :: get_max_fcn_evals => bes_get_max_eval         ! nonlin_multi_eqn_mult_var.f90:302
+        procedure, public :: get_fcn_tolerance => bes_get_fcn_tol          ! :324
+        procedure, public :: get_var_tolerance => bes_get_var_tol          ! :344
+        procedure, public :: get_gradient_tolerance => bes_get_grad_tol    ! :364
         procedure, public :: base_params => bes_params
     end type
 
@@ -221,6 +241,7 @@ module nonlin_batch
     contains
         procedure, public :: set_step_scaling_factor => bls_set_factor
         procedure, public :: solve_batch => lss_solve_batch
+        procedure, public :: solve_sharded => lss_solve_sharded
     end type
 
     !> constrained_least_squares_solver (nonlin_least_squares.f90:34-75): limits, radius, step scaling
@@ -380,6 +401,30 @@ contains
         this%m_gtol = x
     end subroutine
 
+    pure function bes_get_max_eval(this) result(n)
+        class(batch_equation_solver), intent(in) :: this
+        integer(int32) :: n
+        n = this%m_maxEval
+    end function
+
+    pure function bes_get_fcn_tol(this) result(x)
+        class(batch_equation_solver), intent(in) :: this
+        real(real64) :: x
+        x = this%m_fcnTol
+    end function
+
+    pure function bes_get_var_tol(this) result(x)
+        class(batch_equation_solver), intent(in) :: this
+        real(real64) :: x
+        x = this%m_xtol
+    end function
+
+    pure function bes_get_grad_tol(this) result(x)
+        class(batch_equation_solver), intent(in) :: this
+        real(real64) :: x
+        x = this%m_gtol
+    end function
+
     function bes_params(this, fcn) result(p)
         class(batch_equation_solver), intent(in) :: this
         class(batch_vecfcn_helper), intent(in) :: fcn
@@ -452,6 +497,39 @@ contains
         ierr = nlb_least_squares_solve_batch(eng%handle, p, fcn%m_fcn, int(size(x, 1), c_int64_t), &
             int(fcn%m_nfcn, c_int), int(fcn%m_nvar, c_int), c_loc(x), c_loc(fvec), pa, ps, c_loc(ib), &
             c_loc(status), c_null_ptr)
+    end subroutine
+
+    !> The same solve over every engine of `engs` (one per GPU): contiguous system ranges, one host thread per device
+    !> inside the engine, statistics (16 x int64, see NLB_STAT_* in nonlin_batch.h) combined with one NCCL all-reduce.
+    !> x(B, n), fvec(B, m): host arrays.  The reference-side caller is still one `solve` call (nonlin_solver, :94-119).
+    subroutine lss_solve_sharded(this, engs, fcn, x, fvec, ib, status, stats, ierr, args, shared)
+        class(batch_least_squares_solver), intent(in) :: this
+        type(nlb_engine), intent(in), dimension(:) :: engs
+        class(batch_vecfcn_helper), intent(in) :: fcn
+        real(real64), intent(inout), dimension(:,:), contiguous, target :: x
+        real(real64), intent(out), dimension(:,:), contiguous, target :: fvec
+        type(batch_iteration_behavior), intent(out), dimension(:), target :: ib
+        integer(int32), intent(out), dimension(:), target :: status
+        integer(c_int64_t), intent(out), dimension(16), target :: stats
+        integer, intent(out) :: ierr
+        real(real64), intent(in), dimension(:,:), contiguous, target, optional :: args
+        real(real64), intent(in), dimension(:), contiguous, target, optional :: shared
+        type(nlb_params) :: p
+        type(c_ptr) :: pa, ps
+        type(c_ptr), allocatable :: hs(:)
+        integer :: d
+        p = this%base_params(fcn)
+        p%lm_factor = this%m_factor
+        pa = c_null_ptr; ps = c_null_ptr
+        if (present(args)) pa = c_loc(args)
+        if (present(shared)) ps = c_loc(shared)
+        allocate(hs(size(engs)))
+        do d = 1, size(engs)
+            hs(d) = engs(d)%handle
+        end do
+        ierr = nlb_solve_sharded(hs, int(size(engs), c_int), 0_c_int, p, fcn%m_fcn, int(size(x, 1), c_int64_t), &
+            int(fcn%m_nfcn, c_int), int(fcn%m_nvar, c_int), c_loc(x), c_loc(fvec), pa, ps, c_loc(ib), c_loc(status), &
+            c_loc(stats))
     end subroutine
 
     subroutine bcls_set_upper(this, x)

@@ -33,9 +33,12 @@ constexpr int TPS_BLOCK = NLB_TPS_BLOCK;
 // Minimum resident CTAs per SM asked of ptxas.  Measured on B200 (launch-bounds sweep): capping the
 // 2x2 Broyden kernel at 80 registers (6 CTAs/SM) is 11 % faster than 110 registers (4 CTAs/SM); LM is best at
 // 3 CTAs/SM (160 registers); Newton does not gain from a cap.
+#ifndef NLB_LM_MIN_BLOCKS
+#define NLB_LM_MIN_BLOCKS 3
+#endif
 template <int SOLVER>
 constexpr int tps_min_blocks() {
-    return SOLVER == 2 ? 6 : (SOLVER == 0 ? 3 : 1);
+    return SOLVER == 2 ? 6 : (SOLVER == 0 ? NLB_LM_MIN_BLOCKS : 1);
 }
 
 template <class F, int SOLVER>

@@ -43,13 +43,25 @@ struct nlb_handle {
     size_t dwork_cap = 0;
     cudaEvent_t ev_work = nullptr;                 // last kernel that used dwork (orders users on different streams)
     bool work_used = false;
-    cudaStream_t pipe[2] = {nullptr, nullptr};   // copy/compute pipeline for host-resident batches
-    cudaEvent_t ev_in = nullptr, ev_out[2] = {nullptr, nullptr};
+    // pipeline for host-resident batches: upload stream, two kernel streams (alternating, so the last wave of one
+    // chunk's grid overlaps the first of the next), download stream; one event pair per chunk
+    static constexpr int NPIPE = 4, MAXCHUNK = 16;
+    cudaStream_t pipe[NPIPE] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    cudaEvent_t ev_up[MAXCHUNK] = {nullptr}, ev_done[MAXCHUNK] = {nullptr};
     std::mutex mu;
 };
 
 namespace {
 
+
+bool make_chunk_events(nlb_handle* h) {
+    for (int q = 0; q < nlb_handle::MAXCHUNK; ++q)
+        if (cudaEventCreateWithFlags(&h->ev_up[q], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_done[q], cudaEventDisableTiming) != cudaSuccess)
+            return false;
+    return true;
+}
 
 int set_err(nlb_handle* h, int code, const char* what, cudaError_t ce = cudaSuccess) {
     if (h) {
@@ -660,50 +672,61 @@ int solve_batch(nlb_handle* h, int solver, const nlb_params* params, int fcn_id,
         return want_stats ? shard_stats(s) : NLB_OK;
     }
 
-    // Host-resident batch: split it into chunks and pipeline H2D copy / kernel / D2H copy on two
-    // streams, so that the two copy engines and the SMs overlap (the path is PCIe-bound).
-    // Measured on B200 (C2, 2^20 systems, 67 MB back over PCIe; raw pinned D2H of the same bytes 1.2-1.4 ms):
-    // 4 chunks 1.58 ms, 8 chunks 1.68 ms, 16 chunks 1.83 ms, 32 chunks 2.14 ms - per-copy overhead outweighs the
-    // shorter pipeline fill beyond 4.
-    int nchunk = nb >= (1 << 18) ? 4 : (nb >= (1 << 15) ? 2 : 1);
+    // Host-resident batch: split it into chunks and run them through an upload stream, two alternating kernel streams
+    // and a download stream, so that both copy engines (PCIe is full duplex) and the SMs stay busy: chunk c's kernel
+    // waits for its upload only, its download for its kernel only, the upload of chunk c+1 never queues behind a
+    // download, and the last wave of one chunk's grid overlaps the first wave of the next.
+    // Measured on B200, 2^20 systems, pinned buffers (scripts/time_e2e.py), chunks = 2 / 4 / 8 / 16:
+    //   C1 (LM 21x4, 453 MB moved, kernel 6.9 ms)   11.2 / 8.9 / 7.8 / 7.8 ms   (two-stream pipeline before: 10.8 ms)
+    //   C2 (Broyden 2x2, 101 MB, kernel 0.39 ms)    1.67 / 1.64 / 1.60 / - ms
+    //   C3 (Newton refill kernel, 101 MB, 3.0 ms)   3.18 / 3.26 / 3.95 / - ms   (persistent grid: every launch has a tail)
+    const bool refill = solver == SOLVER_NEWTON || solver == SOLVER_CLS;
+    int nchunk = nb >= (1 << 18) ? (refill ? 2 : 8) : (nb >= (1 << 15) ? 2 : 1);
     static const int chunk_override = [] {
         const char* e = std::getenv("NLB_HOST_CHUNKS");      // tuning knob
         return e ? std::atoi(e) : 0;
     }();
     if (chunk_override > 0) nchunk = chunk_override;
+    if (nchunk > nlb_handle::MAXCHUNK) nchunk = nlb_handle::MAXCHUNK;
     const long long chunk = (nb + nchunk - 1) / nchunk;
+    cudaStream_t s_up = h->pipe[0], s_down = h->pipe[2];
     NLB_CUDA(h, cudaEventRecord(h->ev_in, s));
-    for (int q = 0; q < 2; ++q) NLB_CUDA(h, cudaStreamWaitEvent(h->pipe[q], h->ev_in, 0));
+    for (int q = 0; q < nlb_handle::NPIPE; ++q) NLB_CUDA(h, cudaStreamWaitEvent(h->pipe[q], h->ev_in, 0));
     int c = 0;
     for (long long b0 = 0; b0 < nb; b0 += chunk, ++c) {
         const long long cnt = (nb - b0 < chunk) ? (nb - b0) : chunk;
-        cudaStream_t st = h->pipe[c & 1];
         nvtx_push("nlb H2D");
         for (int i = 0; i < 5; ++i) {
             if (a[i].st.staged && a[i].in)
                 NLB_CUDA(h, cudaMemcpy2DAsync((char*)a[i].st.dev + b0 * a[i].elem, (size_t)Bd * a[i].elem,
                                               (const char*)a[i].st.user + b0 * a[i].elem, (size_t)Bh * a[i].elem,
-                                              (size_t)cnt * a[i].elem, a[i].rows, cudaMemcpyHostToDevice, st));
+                                              (size_t)cnt * a[i].elem, a[i].rows, cudaMemcpyHostToDevice, s_up));
         }
+        NLB_CUDA(h, cudaEventRecord(h->ev_up[c], s_up));
         nvtx_pop();
         nvtx_push("nlb solve kernel");
-        rc = launch(b0, cnt, st);
+        cudaStream_t s_run = h->pipe[(c & 1) ? 3 : 1];
+        NLB_CUDA(h, cudaStreamWaitEvent(s_run, h->ev_up[c], 0));
+        rc = launch(b0, cnt, s_run);
         nvtx_pop();
         if (rc) return rc;
+        NLB_CUDA(h, cudaEventRecord(h->ev_done[c], s_run));
         nvtx_push("nlb D2H");
+        NLB_CUDA(h, cudaStreamWaitEvent(s_down, h->ev_done[c], 0));
         for (int i = 0; i < 5; ++i) {
             if (a[i].st.staged && a[i].out)
                 NLB_CUDA(h, cudaMemcpy2DAsync((char*)a[i].st.user + b0 * a[i].elem, (size_t)Bh * a[i].elem,
                                               (const char*)a[i].st.dev + b0 * a[i].elem, (size_t)Bd * a[i].elem,
-                                              (size_t)cnt * a[i].elem, a[i].rows, cudaMemcpyDeviceToHost, st));
+                                              (size_t)cnt * a[i].elem, a[i].rows, cudaMemcpyDeviceToHost, s_down));
         }
         nvtx_pop();
     }
-    for (int q = 0; q < 2; ++q) {
-        NLB_CUDA(h, cudaEventRecord(h->ev_out[q], h->pipe[q]));
-        NLB_CUDA(h, cudaStreamWaitEvent(s, h->ev_out[q], 0));
-    }
+    // the download stream finishes last (it waited for every kernel); the statistics only need the kernels
+    NLB_CUDA(h, cudaEventRecord(h->ev_out, s_down));
+    NLB_CUDA(h, cudaStreamWaitEvent(s, h->ev_done[c - 1], 0));
+    if (c > 1) NLB_CUDA(h, cudaStreamWaitEvent(s, h->ev_done[c - 2], 0));
     if (want_stats && (rc = shard_stats(s))) return rc;
+    NLB_CUDA(h, cudaStreamWaitEvent(s, h->ev_out, 0));
     NLB_CUDA(h, cudaStreamSynchronize(s));
     return NLB_OK;
 }
@@ -731,9 +754,11 @@ int nlb_create(nlb_handle** handle, int device) {
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->pipe[0], cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->pipe[1], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->pipe[2], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->pipe[3], cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_out[0], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_out[1], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming) != cudaSuccess ||
+        !make_chunk_events(h) ||
         cudaMalloc(&h->dstats, sizeof(int64_t) * NLB_STAT_COUNT) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_work, cudaEventDisableTiming) != cudaSuccess ||
         cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
@@ -763,11 +788,14 @@ int nlb_destroy(nlb_handle* h) {
     if (h->dwork) cudaFree(h->dwork);
     if (h->dstats) cudaFree(h->dstats);
     if (h->stream) cudaStreamDestroy(h->stream);
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < nlb_handle::NPIPE; ++q)
         if (h->pipe[q]) cudaStreamDestroy(h->pipe[q]);
-        if (h->ev_out[q]) cudaEventDestroy(h->ev_out[q]);
+    for (int q = 0; q < nlb_handle::MAXCHUNK; ++q) {
+        if (h->ev_up[q]) cudaEventDestroy(h->ev_up[q]);
+        if (h->ev_done[q]) cudaEventDestroy(h->ev_done[q]);
     }
     if (h->ev_in) cudaEventDestroy(h->ev_in);
+    if (h->ev_out) cudaEventDestroy(h->ev_out);
     if (h->ev_work) cudaEventDestroy(h->ev_work);
     delete h;
     return NLB_OK;

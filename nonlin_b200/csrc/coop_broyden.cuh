@@ -5,12 +5,17 @@
 // calls (qr_factor, rank1_update, qr_rank1_update, mtx_mult, solve_triangular_system,
 // recip_mult_array) as the Reference-LAPACK / QRUPDATE algorithms listed in tps_dense.cuh.
 //
-// Mapping.  One CTA of N threads owns one system for its whole solve.  Q and R (N x N, column-major,
-// leading dimension N+1 so that both row-wise and column-wise sweeps are bank-conflict free) and every
-// vector live in shared memory; the Broyden matrix B lives in REGISTERS, thread t holding row t (B is
-// only ever used row-wise - B*dx, the rank-1 update, the forward differences - except for B^T f, which
-// goes through a 4-row staging buffer).  73 KB of shared memory at N = 64: three CTAs per SM.  HBM is
-// touched once to read x0 and once to write x, fvec, ib, status.
+// Mapping.  One CTA of N threads owns one system for its whole solve.  Q (N x N, column-major, leading
+// dimension N+1 so that both row-wise and column-wise sweeps are bank-conflict free), R (packed by columns
+// with room for the sub-diagonal the rank-1 update creates: column j holds rows 0..j+1) and every vector
+// live in shared memory; the Broyden matrix B lives in REGISTERS, thread t holding row t (B is only ever
+// used row-wise - B*dx, the rank-1 update, the forward differences - except for B^T f, which goes through
+// a 4-row staging buffer that aliases the update's work vectors).  54 KB of shared memory at N = 64: four
+// CTAs per SM.  HBM is touched once to read x0 and once to write x, fvec, ib, status.
+//
+// The strictly sequential recurrences (the Givens chain that restores the triangle, the back substitution)
+// run inside one warp at a time with the pivot scalars passed by shuffle instead of through shared memory
+// and a CTA barrier per step; the other warp catches up from shared memory once per 32 steps.
 //
 // Parity.  Every sum keeps the index order of the reference's loop, so results are bit-identical
 // to the CPU oracle.  That is affordable because the O(n^2) kernels parallelise over the
@@ -28,10 +33,17 @@ template <int N>
 struct CoopBroydenSmem {
     static constexpr int LD = N + 1;
     static constexpr int MAT = N * LD;
+    static constexpr int RPK = N * (N + 3) / 2;   // packed upper-Hessenberg storage of R
     static constexpr int NVEC = 10;
-    static constexpr int STAGE = 4;     // rows of B published at a time for B^T f
-    static constexpr size_t BYTES = (2 * (size_t)MAT + (NVEC + STAGE) * (size_t)N) * sizeof(double);
+    static constexpr int STAGE = 4;     // rows of B published at a time for B^T f (aliases s, w, cs, sn)
+    static constexpr int SLD = N + 1;   // their stride (conflict-free for the four owners writing side by side)
+    static constexpr size_t BYTES = ((size_t)MAT + RPK + NVEC * (size_t)N + 8) * sizeof(double);
 };
+
+// offset of column j of the packed R (rows 0..j+1)
+NLB_DEV constexpr int cb_ro(int j) { return j * (j + 3) / 2; }
+template <int N>
+NLB_DEV constexpr unsigned cb_mask() { return N >= 32 ? 0xffffffffu : ((1u << N) - 1u); }
 
 // ---- redundant sequential reductions (identical in every thread) -----------------------
 template <int N>
@@ -47,6 +59,58 @@ NLB_DEV double cb_norm2(const double* a) {
     for (int i = 0; i < N; ++i) acc.add(a[i]);
     return acc.value();
 }
+// NORM2 (libgfortran's one-pass recurrence) with the N divisions spread over the threads: thread i forms the quotient
+// element i meets - its running scale is the largest of 1 and the magnitudes before it - and every thread then replays
+// the ssq recurrence over the N quotients in order.  A quotient is stored as t*t for an ordinary element and as -t for
+// one that raises the scale (same convention as tall_lm.cuh).  wk: N doubles of scratch.  Contains CTA barriers.
+template <int N>
+NLB_DEV double cb_norm2_par(const double* a, double* wk, int tid) {
+    constexpr int NW = (N + 31) / 32;
+    __shared__ double wtot[NW + 1];
+    const unsigned mask = cb_mask<N>();
+    const int lane = tid & 31;
+    const double x = a[tid];
+    const double ax = fabs(x);
+    double inc = (ax == ax) ? ax : 0.0;               // a NaN never becomes the scale (scale < NaN is false)
+#pragma unroll
+    for (int d = 1; d < 32 && d < N; d <<= 1) {
+        const double o = __shfl_up_sync(mask, inc, d);
+        if (lane >= d) inc = (o > inc) ? o : inc;
+    }
+    double before = __shfl_up_sync(mask, inc, 1);
+    if (lane == 0) before = 0.0;
+    if constexpr (N > 32) {
+        if (lane == 31) wtot[tid >> 5] = inc;
+        __syncthreads();
+        double carry = 0.0;
+        for (int w = 0; w < (tid >> 5); ++w) carry = (wtot[w] > carry) ? wtot[w] : carry;
+        before = (carry > before) ? carry : before;
+        inc = (carry > inc) ? carry : inc;
+    }
+    const double sc = (before > 1.0) ? before : 1.0;  // the recurrence starts from scale = 1
+    double qv = 0.0;
+    if (x != 0.0) {
+        const bool up = sc < ax;
+        const double t = (up ? sc : ax) / (up ? ax : sc);
+        qv = up ? -fmax(t, 4.9406564584124654e-324) : t * t;
+    }
+    wk[tid] = qv;
+    if (tid == N - 1) wtot[NW] = (inc > 1.0) ? inc : 1.0;  // final scale
+    __syncthreads();
+    double ssq = 0.0;
+#pragma unroll 8
+    for (int i = 0; i < N; ++i) {
+        const double v = wk[i];
+        const double tt = -v;
+        const double up = 1.0 + ssq * tt * tt;
+        const double ord = ssq + v;
+        ssq = (v < 0.0) ? up : ord;
+    }
+    const double scale = wtot[NW];
+    __syncthreads();                                   // wk and wtot may be reused
+    return scale * sqrt(ssq);
+}
+
 template <int N>
 NLB_DEV double cb_maxabs(const double* a) {
     double t = 0.0;
@@ -98,7 +162,7 @@ NLB_DEV void cb_reflect_trailing(double* a, int i, double tau, int tid) {
 
 // qr_factor(b, q = q, r = r): DGEQR2 on a copy of B, R = upper triangle, Q by DORG2R.
 template <int N>
-NLB_DEV void cb_qr_full(const double (&brow)[N], double* q, double* r, double* tau, int tid) {
+NLB_DEV void cb_qr_full(const double (&brow)[N], double* q, double* r, double* tau, double* sq, int tid) {
     constexpr int LD = N + 1;
 #pragma unroll
     for (int j = 0; j < N; ++j) q[tid + j * LD] = brow[j];
@@ -108,9 +172,32 @@ NLB_DEV void cb_qr_full(const double (&brow)[N], double* q, double* r, double* t
         double t = 0.0, beta = 0.0, sc = 0.0;
         bool scale = false;
         if (N - i > 1) {
-            Dnrm2 acc;
-            for (int rr = i + 1; rr < N; ++rr) acc.add(q[rr + i * LD]);
-            double xnorm = acc.value();
+            // DNRM2 of the sub-column.  Ordinary case - every element zero or inside Blue's middle range: the result is
+            // sqrt of the ordered sum of squares, so thread rr squares element rr and every thread adds the squares in
+            // order (leading zeros add nothing).  Otherwise: the three-accumulator scan, element by element.
+            double xnorm;
+            {
+                const double ax = tid > i ? fabs(q[tid + i * LD]) : 0.0;
+                const bool odd = ax > 0x1p486 || (ax < 0x1p-511 && ax != 0.0);
+                sq[tid] = ax * ax;
+                if (!__syncthreads_or(odd)) {
+                    double amed = 0.0;
+                    if constexpr (N % 8 == 0) {
+#pragma unroll 1
+                        for (int rr = (i + 1) & ~7; rr < N; rr += 8) {
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) amed += sq[rr + u];
+                        }
+                    } else {
+                        for (int rr = i + 1; rr < N; ++rr) amed += sq[rr];
+                    }
+                    xnorm = sqrt(amed);
+                } else {
+                    Dnrm2 acc;
+                    for (int rr = i + 1; rr < N; ++rr) acc.add(q[rr + i * LD]);
+                    xnorm = acc.value();
+                }
+            }
             if (xnorm != 0.0) {
                 double alpha = q[i + i * LD];
                 beta = -nl_sign(dlapy2(alpha, xnorm), alpha);
@@ -155,7 +242,8 @@ NLB_DEV void cb_qr_full(const double (&brow)[N], double* q, double* r, double* t
             __syncthreads();
         }
     }
-    for (int j = 0; j < N; ++j) r[tid + j * LD] = (tid <= j) ? q[tid + j * LD] : 0.0;
+    for (int j = 0; j < N; ++j)
+        if (tid <= j + 1) r[cb_ro(j) + tid] = (tid <= j) ? q[tid + j * LD] : 0.0;
     __syncthreads();
     // DORG2R
     for (int i = N - 1; i >= 0; --i) {
@@ -173,11 +261,14 @@ NLB_DEV void cb_qr_full(const double (&brow)[N], double* q, double* r, double* t
     }
 }
 
-// DQR1UP (full Q): Q R + u v^T -> Q1 R1.  w, cs, sn: N-entry shared work vectors.
+// DQR1UP (full Q): Q R + u v^T -> Q1 R1.  w, cs, sn: N-entry shared work vectors.  R packed (cb_ro).
 template <int N>
 NLB_DEV void cb_qr_rank1_update(double* q, double* r, const double* u, const double* v, double* w, double* cs,
                                 double* sn, int tid) {
     constexpr int LD = N + 1;
+    constexpr int NWARP = (N + 31) / 32;
+    const unsigned mask = cb_mask<N>();
+    const int wid = tid >> 5;
     // w = Q^T u : thread t owns column t of Q
     {
         double s = 0.0;
@@ -190,7 +281,7 @@ NLB_DEV void cb_qr_rank1_update(double* q, double* r, const double* u, const dou
     // DQRTV1: the Givens chain that folds w into w(1), bottom-up (strictly sequential)
     // The chain only needs r of each rotation; it is evaluated (redundantly, uniformly) with the
     // division-free part of DLARTG, the partial r's are kept in sn[], and thread i then computes
-    // c(i), s(i) of its own rotation from the same (f, g) pair — the same values, off the chain.
+    // c(i), s(i) of its own rotation from the same (f, g) pair - the same values, off the chain.
     double w0;
     {
         double rr = w[N - 1];
@@ -208,9 +299,9 @@ NLB_DEV void cb_qr_rank1_update(double* q, double* r, const double* u, const dou
         sn[tid] = s2;
     }
     __syncthreads();
+    double* rc = r + cb_ro(tid);
     // DQRQH: R -> upper Hessenberg, thread t owns column t
     {
-        double* rc = r + tid * LD;
         const int ii = (N - 2 < tid) ? N - 2 : tid;
         double t = rc[ii + 1];
         for (int j = ii; j >= 0; --j) {
@@ -233,29 +324,51 @@ NLB_DEV void cb_qr_rank1_update(double* q, double* r, const double* u, const dou
     }
     __syncthreads();
     // first row of R += w(1) v^T
-    r[tid * LD] = r[tid * LD] + w0 * v[tid];
-    __syncthreads();
-    // DQHQR: back to triangular.  Rotation j is generated from column j once rotations 0..j-1
-    // have been applied to it, then applied to the columns to its right.
+    rc[0] = rc[0] + w0 * v[tid];
+    // DQHQR: back to triangular.  Rotation j is generated from column j once rotations 0..j-1 have been applied to
+    // it, then applied to the columns to its right: a chain of N-1 DLARTGs.  The warp that owns columns 32w..32w+31
+    // runs its 32 links with (c, s) passed by shuffle; the warps to its right apply those 32 rotations from shared
+    // memory afterwards (one CTA barrier per 32 links instead of one per link).
     {
-        double* rc = r + tid * LD;
         double t = rc[0];
-        for (int j = 0; j < N - 1; ++j) {
-            if (tid == j) {
-                double c, s, rjj;
-                dlartg(t, rc[j + 1], c, s, rjj);
-                cs[j] = c; sn[j] = s;
-                rc[j] = rjj;
-                rc[j + 1] = 0.0;
+#pragma unroll 1
+        for (int wv = 0; wv < NWARP; ++wv) {
+            const int j0 = 32 * wv;
+            const int j1 = (j0 + 32 < N - 1) ? j0 + 32 : N - 1;
+            if (wid == wv) {
+#pragma unroll 1
+                for (int j = j0; j < j1; ++j) {
+                    const double rn = (tid >= j) ? rc[j + 1] : 0.0;
+                    double c = 0.0, s = 0.0;
+                    if (tid == j) {
+                        double rjj;
+                        dlartg(t, rn, c, s, rjj);
+                        cs[j] = c; sn[j] = s;
+                        rc[j] = rjj;
+                        rc[j + 1] = 0.0;
+                    }
+                    c = __shfl_sync(mask, c, j & 31);
+                    s = __shfl_sync(mask, s, j & 31);
+                    if (tid > j) {
+                        rc[j] = c * t + s * rn;
+                        t = c * rn - s * t;
+                    }
+                }
             }
-            __syncthreads();
-            if (tid > j) {
-                const double c = cs[j], s = sn[j], rn = rc[j + 1];
-                rc[j] = c * t + s * rn;
-                t = c * rn - s * t;
+            if (NWARP > 1) {
+                __syncthreads();
+                if (wid > wv) {
+#pragma unroll 4
+                    for (int j = j0; j < j1; ++j) {
+                        const double c = cs[j], s = sn[j], rn = rc[j + 1];
+                        rc[j] = c * t + s * rn;
+                        t = c * rn - s * t;
+                    }
+                }
             }
         }
         if (tid == N - 1) rc[N - 1] = t;
+        if (NWARP == 1) __syncthreads();
     }
     // DQROT('F')
     {
@@ -285,8 +398,8 @@ coop_broyden_kernel(DevParams p, long long nsys, long long B, double* __restrict
     constexpr int LD = S::LD;
     extern __shared__ double smem[];
     double* q = smem;
-    double* r = q + S::MAT;
-    double* x = r + S::MAT;
+    double* r = q + S::MAT;   // packed, cb_ro(j) + i
+    double* x = r + S::RPK;
     double* fvec = x + N;
     double* xold = fvec + N;
     double* fvold = xold + N;
@@ -296,7 +409,7 @@ coop_broyden_kernel(DevParams p, long long nsys, long long B, double* __restrict
     double* w = s + N;
     double* cs = w + N;
     double* sn = cs + N;
-    double* stage = sn + N;   // STAGE x N staging rows for B^T f
+    double* stage = s;        // STAGE x SLD staging rows for B^T f: s, w, cs, sn (+ 8 spare doubles) are dead by then
     double* tau = w;          // Householder scalars: only live inside the refactorisation
     double* xp = s;           // perturbed copy of x for the forward differences: only live there too
     double brow[N];           // row `tid` of the Broyden matrix B
@@ -342,7 +455,7 @@ coop_broyden_kernel(DevParams p, long long nsys, long long B, double* __restrict
                 }
                 ++njac;
                 __syncthreads();
-                cb_qr_full<N>(brow, q, r, tau, tid);
+                cb_qr_full<N>(brow, q, r, tau, cs, tid);
                 jcount = 0;
             } else {
                 df[tid] = fvec[tid] - fvold[tid];
@@ -388,13 +501,13 @@ coop_broyden_kernel(DevParams p, long long nsys, long long B, double* __restrict
                 constexpr int ST = S::STAGE < N ? S::STAGE : N;
                 for (int i0 = 0; i0 < N; i0 += ST) {
                     if (tid >= i0 && tid < i0 + ST) {
-                        double* dst = stage + (tid - i0) * N;
+                        double* dst = stage + (tid - i0) * S::SLD;
 #pragma unroll
                         for (int j = 0; j < N; ++j) dst[j] = brow[j];
                     }
                     __syncthreads();
 #pragma unroll
-                    for (int u = 0; u < ST; ++u) t1 += stage[u * N + tid] * fvec[i0 + u];
+                    for (int u = 0; u < ST; ++u) t1 += stage[u * S::SLD + tid] * fvec[i0 + u];
                     __syncthreads();
                 }
                 const double* qc = q + tid * LD;
@@ -408,14 +521,46 @@ coop_broyden_kernel(DevParams p, long long nsys, long long B, double* __restrict
             }
             fold = f;
             __syncthreads();
-            // R step = -Q^T F (DTRSV upper, no-trans, non-unit)
-            for (int j = N - 1; j >= 0; --j) {
-                const double xj = df[j];
-                if (xj != 0.0) {
-                    const double t = xj / r[j + j * LD];
-                    __syncthreads();
-                    if (tid < j) df[tid] = df[tid] - t * r[tid + j * LD];
-                    if (tid == j) df[j] = t;
+            // R step = -Q^T F (DTRSV upper, no-trans, non-unit): a chain of N divisions.  Thread i keeps entry i in a
+            // register; the warp that owns rows 32w..32w+31 runs its 32 links with the pivot entry passed by shuffle
+            // (every lane forms the same quotient), then publishes them, and the warps above it apply those 32 columns
+            // to their rows from shared memory - one CTA barrier per 32 links.
+            {
+                constexpr int NWARP = (N + 31) / 32;
+                __shared__ unsigned solved_nz[NWARP];
+                const unsigned mask = cb_mask<N>();
+                const int wid = tid >> 5;
+                double v = df[tid];
+#pragma unroll 1
+                for (int wv = NWARP - 1; wv >= 0; --wv) {
+                    const int j0 = 32 * wv;
+                    const int j1 = (j0 + 31 < N - 1) ? j0 + 31 : N - 1;
+                    if (wid == wv) {
+                        unsigned nz = 0;
+#pragma unroll 1
+                        for (int j = j1; j >= j0; --j) {
+                            const double xj = __shfl_sync(mask, v, j & 31);
+                            if (xj != 0.0) {
+                                const double* rcol = r + cb_ro(j);
+                                const double t = xj / rcol[j];
+                                if (tid < j) v = v - t * rcol[tid];
+                                if (tid == j) v = t;
+                                nz |= 1u << (j & 31);
+                            }
+                        }
+                        df[tid] = v;
+                        if ((tid & 31) == 0) solved_nz[wv] = nz;
+                    }
+                    if (wv > 0) {
+                        __syncthreads();
+                        if (wid < wv) {
+                            const unsigned nz = solved_nz[wv];
+#pragma unroll 4
+                            for (int j = j1; j >= j0; --j) {
+                                if ((nz >> (j & 31)) & 1u) v = v - df[j] * r[cb_ro(j) + tid];
+                            }
+                        }
+                    }
                 }
                 __syncthreads();
             }
@@ -429,8 +574,7 @@ coop_broyden_kernel(DevParams p, long long nsys, long long B, double* __restrict
                 if (temp > stpmax) df[tid] = df[tid] * (stpmax / temp);
                 __syncthreads();
                 {   // limit_search_vector
-                    const double mag = cb_norm2<N>(df);
-                    __syncthreads();
+                    const double mag = cb_norm2_par<N>(df, w, tid);
                     if (mag != 0.0 && mag > stpmax) df[tid] = (stpmax / mag) * df[tid];
                     __syncthreads();
                 }

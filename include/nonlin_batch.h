@@ -179,8 +179,10 @@ void nlb_constrained_options_default(nlb_constrained_options* o);
 
 /* constrained_least_squares_solver%solve  (cls_solve, src/nonlin_least_squares.f90:938-1176; dogleg :1301-1403,
  * coleman_li_scaling :1222-1260, alpha_box :1181-1219, ces_apply_limits :858-883) over B systems.  Arguments as
- * nlb_least_squares_solve_batch.  Available for the fixed-size residuals (m, n reported non-zero by
- * nlb_vecfcn_info, n <= 8); others return NLB_ERR_UNSUPPORTED.  status[b] = 0 or NLB_CONVERGENCE_ERROR (:1173-1175);
+ * nlb_least_squares_solve_batch.  Available for the built-in residuals with n <= 16: the fixed-size ones (m, n
+ * reported non-zero by nlb_vecfcn_info) and the curve-fit families with a run-time number of observations m (their
+ * m-sized state lives in a device workspace capped at 4 GB; a batch x m that cannot be served within it returns
+ * NLB_ERR_UNSUPPORTED, as plug-in residuals do).  status[b] = 0 or NLB_CONVERGENCE_ERROR (:1173-1175);
  * a system whose start (after clamping to the limits) or first residual is NaN or +-huge returns status 0 with an
  * all-zero iteration_behavior, as the reference's early `return` does (:1043-1045). */
 int nlb_constrained_least_squares_solve_batch(nlb_handle* handle, const nlb_params* params,

@@ -6,6 +6,7 @@
 #include "coop_lm.cuh"
 #include "coop_lm_cta.cuh"
 #include "tall_lm.cuh"
+#include "cls_rt.cuh"
 
 #include <cstdlib>
 
@@ -226,6 +227,42 @@ int launch_coop_solve(int solver, int fcn_id, const DevParams& p, long long nsys
     }
     if (solver == SOLVER_LM) return launch_coop_lm(fcn_id, p, nsys, B, m, n, x, fvec, sys, shared, ib, status, s, launches);
     return NLB_ERR_UNSUPPORTED;
+}
+
+namespace {
+template <class F>
+int launch_cls_rt(const DevParams& p, const DevCls& o, long long nsys, long long B, int m, double* x, double* fvec,
+                  const double* sys, const double* shared, nlb_iteration_behavior* ib, int32_t* status, cudaStream_t s,
+                  int64_t* launches) {
+    KernelCfg cfg;
+    if (kernel_cfg<cls_rt_kernel<F>>(128, 0, &cfg) != cudaSuccess) return NLB_ERR_CUDA;
+    const long long per = cls_rt_ws_doubles<F::N>(m) * (long long)sizeof(double);
+    long long T = (long long)cfg.num_sms * cfg.ctas_per_sm * 128;
+    const long long need = ((nsys + 127) / 128) * 128;
+    if (T > need) T = need;
+    const long long budget = 4LL << 30;          // workspace cap: fewer threads (grid-stride) rather than more memory
+    while (T > 128 && T * per > budget) T -= 128;
+    if (T * per > budget) return NLB_ERR_UNSUPPORTED;
+    double* ws = nullptr;
+    if (cudaMallocAsync((void**)&ws, (size_t)(T * per), s) != cudaSuccess) return NLB_ERR_CUDA;
+    cls_rt_kernel<F><<<(unsigned)(T / 128), 128, 0, s>>>(p, o, nsys, B, m, x, fvec, sys, shared, ib, status, ws);
+    ++*launches;
+    const cudaError_t le = cudaGetLastError();
+    if (cudaFreeAsync(ws, s) != cudaSuccess || le != cudaSuccess) return NLB_ERR_CUDA;
+    return NLB_OK;
+}
+}  // namespace
+
+int launch_coop_cls(int fcn_id, const DevParams& p, const DevCls& o, long long nsys, long long B, int m, int n, double* x,
+                    double* fvec, const double* sys, const double* shared, nlb_iteration_behavior* ib, int32_t* status,
+                    cudaStream_t s, int64_t* launches) {
+    (void)n;
+    switch (fcn_id) {
+        case FCN_RATIONAL_7_8: return launch_cls_rt<Rational78>(p, o, nsys, B, m, x, fvec, sys, shared, ib, status, s, launches);
+        case FCN_EXP_SUM_8: return launch_cls_rt<ExpSum8>(p, o, nsys, B, m, x, fvec, sys, shared, ib, status, s, launches);
+        case FCN_EXP_DECAY_4: return launch_cls_rt<ExpDecay4>(p, o, nsys, B, m, x, fvec, sys, shared, ib, status, s, launches);
+        default: return NLB_ERR_UNSUPPORTED;
+    }
 }
 
 int launch_coop_eval(int fcn_id, long long B, int m, int n, const double* x, double* fvec, const double* sys,

@@ -638,9 +638,14 @@ int solve_batch(nlb_handle* h, int solver, const nlb_params* params, int fcn_id,
             if (r == NLB_ERR_CUDA) return set_err(h, r, "plug-in kernel launch", cudaGetLastError());
             if (r != NLB_OK) return set_err(h, r, "the plug-in residual does not serve this solver");
         } else if (solver == SOLVER_CLS) {
-            r = (fi.m != 0 && fi.n != 0)
-                    ? dispatch_cls(h, fcn_id, p, *cls, cnt, Bd, dx, df, ds, dsh, dib, dst, st)
-                    : set_err(h, NLB_ERR_UNSUPPORTED, "constrained least squares: fixed-size residuals only");
+            if (fi.m != 0 && fi.n != 0) {
+                r = dispatch_cls(h, fcn_id, p, *cls, cnt, Bd, dx, df, ds, dsh, dib, dst, st);
+            } else {
+                r = launch_coop_cls(fcn_id, p, *cls, cnt, Bd, m, n, dx, df, ds, dsh, dib, dst, st, &h->launches);
+                if (r == NLB_ERR_UNSUPPORTED)
+                    return set_err(h, r, "constrained least squares: no kernel for this residual / size (workspace cap 4 GB)");
+                if (r == NLB_ERR_CUDA) return set_err(h, r, "constrained least squares kernel launch", cudaGetLastError());
+            }
         } else if (fi.m != 0 && fi.n != 0) {
             switch (solver) {
                 case SOLVER_LM: r = dispatch_tps<SOLVER_LM>(h, fcn_id, p, cnt, Bd, dx, df, ds, dsh, dib, dst, st); break;
@@ -903,7 +908,7 @@ int nlb_constrained_least_squares_solve_batch(nlb_handle* h, const nlb_params* p
     FcnInfo fi;
     if (!fcn_info(fcn_id, &fi)) return set_err(h, NLB_ERR_UNKNOWN_FCN, "unknown residual id");
     const int nv = fi.n != 0 ? fi.n : n;
-    if (nv <= 0 || nv > CLS_MAX_N) return set_err(h, NLB_ERR_UNSUPPORTED, "constrained least squares: n <= 8");
+    if (nv <= 0 || nv > CLS_MAX_N) return set_err(h, NLB_ERR_UNSUPPORTED, "constrained least squares: n <= 16");
     DevCls o;
     // cls_set_radius / cls_set_factor: a non-positive value selects 1 (least_squares:902-909, 927-934)
     o.radius = options->trust_region_radius > 0.0 ? options->trust_region_radius : 1.0;

@@ -24,7 +24,7 @@
 
 namespace nlb {
 
-constexpr int CLS_MAX_N = 8;
+constexpr int CLS_MAX_N = 16;
 
 // constrained_least_squares_solver's own members and the limit arrays of constrained_equation_solver.
 struct DevCls {

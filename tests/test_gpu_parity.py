@@ -539,10 +539,12 @@ def test_non_finite_and_degenerate_starts_terminate_like_the_oracle(engine, orac
 # constrained_least_squares_solver: bounded trust-region dogleg
 # ---------------------------------------------------------------------------------------------
 def run_cls(nb, oracle, fcn, x0, m, args=None, lower=None, upper=None, radius=None, scaling=None, analytic=False,
-            **params):
+            shared=None, **params):
     n, B = x0.shape
     obj = nb.vecfcn_helper()
     obj.set_fcn(fcn, m, n)
+    if shared is not None:
+        obj.set_shared_data(shared)
     if analytic:
         obj.set_jacobian()
     s = nb.constrained_least_squares_solver()
@@ -561,7 +563,7 @@ def run_cls(nb, oracle, fcn, x0, m, args=None, lower=None, upper=None, radius=No
     f = np.zeros((m, B))
     ib = nb.iteration_behavior(B)
     st = s.solve(obj, x, f, ib, args=args)
-    ref = oracle.cls_solve_batch(fcn, x0, m=m, sys=args, lower=lower, upper=upper, trust_region_radius=radius,
+    ref = oracle.cls_solve_batch(fcn, x0, m=m, sys=args, shared=shared, lower=lower, upper=upper, trust_region_radius=radius,
                                  step_scaling_factor=scaling,
                                  params=oracle.params(use_analytic_jacobian=int(analytic), **params))
     return (x, f, ib, st), ref
@@ -738,11 +740,37 @@ def test_cls_unsupported_residual_is_an_api_error(engine):
     import nonlin_b200 as nb
 
     obj = nb.vecfcn_helper()
-    obj.set_fcn("exp_decay_4", 64, 4)
-    obj.set_shared_data(np.linspace(0.0, 4.0, 64))
+    obj.set_fcn("ext_rosenbrock", 8, 8)
     with pytest.raises(nb.NonlinError) as e:
-        nb.constrained_least_squares_solver().solve(obj, np.ones((4, 8)), args=np.ones((64, 8)))
+        nb.constrained_least_squares_solver().solve(obj, np.ones((8, 8)))
     assert e.value.code == nb.NLB_ERR_UNSUPPORTED
+
+
+CLS_RT_CASES = [
+    # residual family, m, batch, lower, upper, max evals
+    ("exp_decay_4", 64, 1024, None, None, 200),
+    ("exp_decay_4", 64, 1024, [0.0, 0.0, 0.0, 0.0], [2.5, 0.5, 1.2, 2.5], 200),     # bounds active for part of the batch
+    ("exp_decay_4", 33, 257, [0.5] * 4, None, 60),                                   # ragged sizes, one-sided, budget hit
+    ("rational_7_8", 96, 200, None, None, 100),                                      # n = 16 (limit arrays of 16)
+    ("rational_7_8", 576, 40, [-2.0] * 16, [2.0] * 16, 60),
+]
+
+
+@pytest.mark.parametrize("fcn,m,B,lower,upper,maxeval", CLS_RT_CASES)
+def test_cls_runtime_m_families_parity_vs_oracle(engine, oracle, fcn, m, B, lower, upper, maxeval):
+    """constrained_least_squares_solver on the curve-fit families (run-time m; csrc/cls_rt.cuh): bit for bit against
+    the oracle, counters and status included (VERDICT r1 "missing" #2)."""
+    import nonlin_b200 as nb
+    from nonlin_b200 import workloads as W
+
+    w = W.lm_expdecay4(B, m=m) if fcn == "exp_decay_4" else W.c4_lm_rational(B, m=m, noise=1e-3)
+    got, ref = run_cls(nb, oracle, fcn, w["x0"], m, args=w["args"], shared=w["shared"], lower=lower, upper=upper,
+                       max_fcn_evals=maxeval)
+    assert_identical(got, ref)
+    st = ref[3]
+    assert (st == 0).any() or maxeval < 100          # (the 60-evaluation cases exist to end on the budget)
+    if lower is not None:
+        assert np.all(got[0] >= np.array(lower)[:, None])
 
 
 def test_lm_shared_memory_jacobian_variant_is_bit_identical(engine):

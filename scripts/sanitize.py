@@ -31,6 +31,15 @@ cases = {
     "tps_lm": lambda: run(W.c1_lm_polyfit(1000)),
     "broyden2": lambda: run(W.c2_broyden_2x2(3000)),
 }
+def cls_rt():
+    """constrained least squares on a run-time-m family (cls_rt.cuh: HBM workspace)"""
+    w = W.lm_expdecay4(300, m=33)
+    obj = nb.vecfcn_helper(); obj.set_fcn(w["fcn"], w["m"], w["n"]); obj.set_shared_data(w["shared"])
+    s = nb.constrained_least_squares_solver(); s.set_max_fcn_evals(60); s.set_lower_limits([0.5] * 4)
+    x = w["x0"].copy(); f = np.zeros((w["m"], 300)); ib = nb.iteration_behavior(300)
+    st = s.solve(obj, x, f, ib, args=w["args"])
+    return int((st == 0).sum()), int(ib["iter_count"].sum())
+cases["cls_rt"] = cls_rt
 def polyfit():
     p = nb.polynomial()
     w = W.c1_lm_polyfit(700)

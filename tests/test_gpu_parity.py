@@ -293,6 +293,31 @@ def test_host_and_device_buffers_give_the_same_bits(engine):
     assert engine.reduce_stats(ib, st) == stats     # host arrays in, same numbers
 
 
+@pytest.mark.parametrize("name,B", [("C1", 40001), ("C2", 300007), ("C3", 262144 + 5), ("C1", 262144 + 129)])
+def test_chunked_host_pipeline_equals_device_path(engine, name, B):
+    """Host-resident batches of 2^15 systems and more go through the four-stream chunk pipeline (upload / two kernel
+    streams / download, nlb_api.cu solve_batch): 2 chunks from 2^15, 8 from 2^18 (2 for the persistent Newton kernel).
+    Ragged sizes, every output array, against the one-launch device-buffer path: same bits."""
+    import torch
+
+    import nonlin_b200 as nb
+    from nonlin_b200 import workloads as W
+
+    w = W.WORKLOADS[name](B)
+    x, f, ib, st = run_engine(nb, w)                     # numpy in, numpy out: the host path
+    obj = nb.vecfcn_helper(); obj.set_fcn(w["fcn"], w["m"], w["n"])
+    s = make_solver(nb, w)
+    xd = torch.from_numpy(w["x0"]).cuda()
+    ad = None if w["args"] is None else torch.from_numpy(w["args"]).cuda()
+    fd = torch.empty((w["m"], B), dtype=torch.float64, device="cuda")
+    ibd = nb.iteration_behavior(B, like=xd)
+    std = s.solve(obj, xd, fd, ibd, args=ad)
+    torch.cuda.synchronize()
+    assert np.array_equal(xd.cpu().numpy(), x) and np.array_equal(fd.cpu().numpy(), f)
+    assert np.array_equal(nb.ib_view(ibd), ib) and np.array_equal(std.cpu().numpy(), st)
+    assert int((st == 0).sum()) == B
+
+
 # ---------------------------------------------------------------------------------------------
 # full BASELINE sizes: size-independent properties
 # ---------------------------------------------------------------------------------------------

@@ -76,8 +76,27 @@ inline real f_sign(real a, real b) { return real(std::copysign(std::fabs(dval(a)
 inline real f_max(real a, real b) { return (b > a || f_isnan(a)) ? b : a; }
 inline real f_min(real a, real b) { return (b < a || f_isnan(a)) ? b : a; }
 
+// STUDY SWITCH - not the reference's arithmetic (default 0 = off; nothing in the test-suite turns it on).
+// Mode 1 evaluates every long sum (64 terms or more: the m-length norms and dot products of the LM path) in the order a
+// warp-shuffle reduction would: lane l adds terms l, l+32, l+64, ..., then a butterfly adds the 32 partial sums; norms
+// become sqrt of the plain sum of squares.  scripts/striped_sum_study.py uses it to measure how far iteration counts
+// and results move when the summation order is not the reference's (VERDICT r1 #2a / SURVEY 7 option i).
+void nl_set_sum_mode(int mode);
+int nl_get_sum_mode();
+template <class Term>
+inline real f_striped_sum(int n, Term term) {
+    real part[32];
+    for (int l = 0; l < 32; ++l) part[l] = 0.0;
+    for (int i = 0; i < n; ++i) part[i & 31] += term(i);
+    for (int d = 16; d >= 1; d >>= 1)
+        for (int l = 0; l < d; ++l) part[l] += part[l + d];
+    return part[0];
+}
+
 // libgfortran norm2_r8: one pass, running scale and scaled sum of squares.
 inline real f_norm2(const real* v, int n, int stride = 1) {
+    if (n >= 64 && nl_get_sum_mode() == 1)
+        return f_sqrt(f_striped_sum(n, [&](int i) { const real x = v[(long)i * stride]; return x * x; }));
     real scale = 1.0;
     real ssq = 0.0;
     for (int i = 0; i < n; ++i) {
@@ -99,6 +118,7 @@ inline real f_norm2(const real* v, int n, int stride = 1) {
 
 // Sequential dot product, index order, as an inlined Fortran DOT_PRODUCT.
 inline real f_dot(const real* a, const real* b, int n) {
+    if (n >= 64 && nl_get_sum_mode() == 1) return f_striped_sum(n, [&](int i) { return a[i] * b[i]; });
     real s = 0.0;
     for (int i = 0; i < n; ++i) s += a[i] * b[i];
     return s;

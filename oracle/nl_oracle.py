@@ -155,6 +155,10 @@ class Oracle:
             setattr(p, k, v)
         return p
 
+    def set_sum_mode(self, mode):
+        """STUDY SWITCH (not the reference's arithmetic): 1 = long sums in warp-shuffle (striped + butterfly) order."""
+        self.lib.nlo_set_sum_mode(int(mode))
+
     def set_libm_exp(self, on):
         self.lib.nlo_set_libm_exp(int(bool(on)))
 

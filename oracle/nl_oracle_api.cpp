@@ -24,6 +24,9 @@ namespace nlo {
 static int g_libm_exp = 0;
 void nl_set_libm_exp(int on) { g_libm_exp = on; }
 int nl_get_libm_exp() { return g_libm_exp; }
+static int g_sum_mode = 0;
+void nl_set_sum_mode(int mode) { g_sum_mode = mode; }
+int nl_get_sum_mode() { return g_sum_mode; }
 #ifdef NL_COUNT_FLOPS
 thread_local unsigned long long g_flops = 0;
 #endif
@@ -70,6 +73,7 @@ unsigned long long nlo_flops_total(void) { return g_flops_total.load(); }
 void nlo_flops_reset(void) { g_flops_total.store(0); }
 
 void nlo_set_libm_exp(int on) { nl_set_libm_exp(on); }
+void nlo_set_sum_mode(int mode) { nl_set_sum_mode(mode); }
 
 int nlo_fcn_lookup(const char* name) {
     const Problem* p = nl_problem_by_name(name);

@@ -218,8 +218,7 @@ void lm_factor(int m, int n, real* a, bool pivot, int* ipvt, real* rdiag, real* 
             const int jp1 = j + 1;
             if (n >= jp1) {
                 for (int k = jp1; k <= n; ++k) {      // :652-662
-                    real sm = ZERO;
-                    for (int i = j; i <= m; ++i) sm += M2(a, m, i, j) * M2(a, m, i, k);
+                    real sm = f_dot(&M2(a, m, j, j), &M2(a, m, j, k), m - j + 1);   // sequential, i = j..m
                     real temp = sm / M2(a, m, j, j);
                     for (int i = j; i <= m; ++i) M2(a, m, i, k) = M2(a, m, i, k) - temp * M2(a, m, i, j);
                     if (!pivot || V(rdiag, k) == ZERO) continue;
@@ -441,8 +440,7 @@ int lm_solve(const Problem* p, const FcnCtx* c, const Params* prm, real* x, real
         for (int i = 1; i <= neqn; ++i) V(wa4, i) = V(fvec, i);   // :241-253
         for (int j = 1; j <= nvar; ++j) {
             if (M2(jac, neqn, j, j) != zero) {
-                real sm = zero;
-                for (int i = j; i <= neqn; ++i) sm += M2(jac, neqn, i, j) * V(wa4, i);
+                real sm = f_dot(&M2(jac, neqn, j, j), &V(wa4, j), neqn - j + 1);   // sequential, i = j..neqn
                 temp = -sm / M2(jac, neqn, j, j);
                 for (int i = j; i <= neqn; ++i) V(wa4, i) = V(wa4, i) + M2(jac, neqn, i, j) * temp;
             }

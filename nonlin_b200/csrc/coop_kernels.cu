@@ -293,3 +293,12 @@ int launch_coop_jacobian(int fcn_id, long long B, int m, int n, const double* x,
 }
 
 }  // namespace nlb
+
+#ifdef NLB_TLM_TRACE
+// debug build only (scripts/tlm_trace.py): copy the clock stamps of tall_lm.cuh's probes back
+extern "C" int nlb_debug_tlm_trace(long long* stamps, int* counts) {
+    if (cudaMemcpyFromSymbol(stamps, nlb::tlm_trace_buf, sizeof(long long) * 16 * 512) != cudaSuccess) return 1;
+    (void)counts;
+    return 0;
+}
+#endif

@@ -215,11 +215,48 @@ struct Rational78 {
         den = 1.0 + t * den;
         return num / den - y;
     }
+    // The residual is a quotient of two Horner chains and a forward-difference column changes a coefficient of one of
+    // them only: parts() gives the two chains of the unperturbed point, residual_pert_parts() re-evaluates the chain that
+    // contains x[c] and reuses the other (the same operations on the same values: the same bits as residual_pert).
+    static constexpr bool SPLIT = true;
+    NLB_DEV static void parts(const double* x, double t, double& num, double& den) {
+        num = x[7];
+#pragma unroll
+        for (int k = 6; k >= 0; --k) num = num * t + x[k];
+        den = x[15];
+#pragma unroll
+        for (int k = 14; k >= 8; --k) den = den * t + x[k];
+        den = 1.0 + t * den;
+    }
+    // PART = 0: x[c] is a numerator coefficient (c < SPLIT_AT), PART = 1: a denominator coefficient
+    static constexpr int SPLIT_AT = 8;
+    template <int PART>
+    NLB_DEV static double residual_pert_part(const double* x, int c, double xc, double t, double y, double num0, double den0) {
+        double num = num0, den = den0;
+        if constexpr (PART == 0) {
+            num = (c == 7) ? xc : x[7];
+#pragma unroll
+            for (int k = 6; k >= 0; --k) num = num * t + ((c == k) ? xc : x[k]);
+        } else {
+            den = (c == 15) ? xc : x[15];
+#pragma unroll
+            for (int k = 14; k >= 8; --k) den = den * t + ((c == k) ? xc : x[k]);
+            den = 1.0 + t * den;
+        }
+        return num / den - y;
+    }
 };
 
 // sum of 8 exponentials, x = [a0..a7, b0..b7]         (BASELINE config 4 throughput model)
 struct ExpSum8 {
     static constexpr int ID = FCN_EXP_SUM_8, N = 16;
+    static constexpr bool SPLIT = false;
+    NLB_DEV static void parts(const double*, double, double&, double&) {}
+    static constexpr int SPLIT_AT = 16;
+    template <int PART>
+    NLB_DEV static double residual_pert_part(const double* x, int c, double xc, double t, double y, double, double) {
+        return residual_pert(x, c, xc, t, y);
+    }
     NLB_DEV static double residual(const double* x, double t, double y) { return residual_pert(x, -1, 0.0, t, y); }
     // one exponential per trip of a rolled loop (eight inlined copies of nl_exp cost 20 k instructions per kernel);
     // the parameters are picked out of registers by select chains

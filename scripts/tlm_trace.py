@@ -18,7 +18,7 @@ lib = ctypes.CDLL(os.environ["NLB_LIB"])
 stamps = np.zeros((16, 512), dtype=np.int64); counts = np.zeros(8, dtype=np.int32)
 rc = lib.nlb_debug_tlm_trace(stamps.ctypes.data_as(ctypes.c_void_p), counts.ctypes.data_as(ctypes.c_void_p))
 print("rc", rc)
-names = ["P:full_in", "P:empty_p", "P:rowop", "P:bar1", "IO:done", "C:full_p", "C:summed", "c:v=a/ajn", "c:updated", "c:bar2", "c:swapped", "c:scan_a", "c:bar3", "c:quot"]
+names = ["P:full_in", "P:empty_p", "P:rowop", "P:bar1", "IO:done", "C:full_p", "C:summed", "probe7", "probe8", "probe9", "probe10", "probe11", "probe12", "probe13"]
 n = 128
 t0 = stamps[0, 0]
 half = n // 2

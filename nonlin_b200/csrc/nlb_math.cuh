@@ -116,31 +116,6 @@ NLB_DEV void iset(int (&v)[N], int idx, int val) {
     }
 }
 
-// ---- IEEE division without its branch ----------------------------------------------------
-// nvcc expands a / b on doubles to: reciprocal seed (MUFU.RCP64H, low word 1), two Newton refinements, q = a*y,
-// r = fma(-b, q, a), q' = fma(r, y, q), then two range tests on the high words of a and q' and a BRANCH to an out-of-line
-// routine when they fail.  That branch keeps the scheduler from overlapping several independent divisions.  nl_div_try is the
-// same arithmetic and the same two tests without the branch: `ok` says whether the compiler's own fast path would have
-// been taken, in which case the quotient is, bit for bit, what a / b gives; the caller redoes the divisions of a batch
-// with `/` when any `ok` is false (denormal or huge operands, zero or non-finite divisors).
-NLB_DEV double nl_div_try(double a, double b, bool& ok) {
-    double y0;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(b));
-    double y = __hiloint2double(__double2hiint(y0), 1);
-    double e = __fma_rn(-b, y, 1.0);
-    e = __fma_rn(e, e, e);
-    y = __fma_rn(y, e, y);
-    e = __fma_rn(-b, y, 1.0);
-    y = __fma_rn(y, e, y);
-    double q = __dmul_rn(y, a);
-    const double r = __fma_rn(-b, q, a);
-    q = __fma_rn(y, r, q);
-    const float ah = __int_as_float(__double2hiint(a)), bh = __int_as_float(__double2hiint(b));
-    const float qh = __int_as_float(__double2hiint(q));
-    ok = (fabsf(ah) >= 6.5827683646048100446e-37f) && (fabsf(__fmaf_rn(0.0f, bh, qh)) > 1.469367938527859385e-39f);
-    return q;
-}
-
 // ---- software exp --------------------------------------------------------------------
 NLB_DEV double nl_exp(double x) {
     const double LN2_HI = 6.93147180369123816490e-01;

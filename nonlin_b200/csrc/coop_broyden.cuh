@@ -26,8 +26,19 @@
 // which keeps all scalars and the control flow uniform without broadcasts.
 #pragma once
 #include "tps_common.cuh"
+#include "nlb_div.cuh"
 
 namespace nlb {
+
+#ifdef NLB_CB_TRACE
+// debug build only: clock stamps of thread 0 of CTA 0 at the phase boundaries of every iteration (scripts/cb_trace.py)
+__device__ long long cb_trace_buf[64][32];
+#define CB_TRACE(probe) do { if (blockIdx.x == 0 && tid == 0 && iter < 64) cb_trace_buf[iter][probe] = clock64(); } while (0)
+#define CB_TRACE2(probe) do { if (blockIdx.x == 0 && tid == 0 && cb_it < 64) cb_trace_buf[cb_it][16 + (probe)] = clock64(); } while (0)
+#else
+#define CB_TRACE(probe) do { } while (0)
+#define CB_TRACE2(probe) do { } while (0)
+#endif
 
 template <int N>
 struct CoopBroydenSmem {
@@ -116,6 +127,24 @@ NLB_DEV double cb_maxabs(const double* a) {
     double t = 0.0;
     for (int i = 0; i < N; ++i) t = nl_max(fabs(a[i]), t);
     return t;
+}
+
+// DLARTG for the re-triangularisation chain: the ordinary branch forms its two quotients (c = |f| / d, s = g / r) with the
+// branch-free division, so that they overlap instead of running one after the other; same values as dlartg().
+NLB_DEV void cb_dlartg(double f, double g, double& c, double& s, double& r) {
+    const double rtmin = 0x1p-511, rtmax = 0x1.6a09e667f3bcdp+510;
+    const double f1 = fabs(f), g1 = fabs(g);
+    if (g != 0.0 && f != 0.0 && f1 > rtmin && f1 < rtmax && g1 > rtmin && g1 < rtmax) {
+        const double d = sqrt(f * f + g * g);
+        r = nl_sign(d, f);
+        bool ok1, ok2;
+        const double cq = nl_div_try(f1, d, ok1);
+        const double sq = nl_div_try(g, r, ok2);
+        if (ok1 && ok2) { c = cq; s = sq; }
+        else { c = f1 / d; s = g / r; }
+    } else {
+        dlartg(f, g, c, s, r);
+    }
 }
 
 // DLARF('L'): H = I - tau v v^T with v = column i of a (a(i,i) == 1) applied to columns c > i.
@@ -264,7 +293,8 @@ NLB_DEV void cb_qr_full(const double (&brow)[N], double* q, double* r, double* t
 // DQR1UP (full Q): Q R + u v^T -> Q1 R1.  w, cs, sn: N-entry shared work vectors.  R packed (cb_ro).
 template <int N>
 NLB_DEV void cb_qr_rank1_update(double* q, double* r, const double* u, const double* v, double* w, double* cs,
-                                double* sn, int tid) {
+                                double* sn, int tid, int cb_it = 64) {
+    (void)cb_it;
     constexpr int LD = N + 1;
     constexpr int NWARP = (N + 31) / 32;
     const unsigned mask = cb_mask<N>();
@@ -278,6 +308,7 @@ NLB_DEV void cb_qr_rank1_update(double* q, double* r, const double* u, const dou
         w[tid] = s;
     }
     __syncthreads();
+    CB_TRACE2(0);
     // DQRTV1: the Givens chain that folds w into w(1), bottom-up (strictly sequential)
     // The chain only needs r of each rotation; it is evaluated (redundantly, uniformly) with the
     // division-free part of DLARTG, the partial r's are kept in sn[], and thread i then computes
@@ -292,6 +323,7 @@ NLB_DEV void cb_qr_rank1_update(double* q, double* r, const double* u, const dou
         w0 = rr;
     }
     __syncthreads();
+    CB_TRACE2(1);
     if (tid < N - 1) {
         double c, s2, t;
         dlartg(w[tid], sn[tid], c, s2, t);
@@ -299,6 +331,7 @@ NLB_DEV void cb_qr_rank1_update(double* q, double* r, const double* u, const dou
         sn[tid] = s2;
     }
     __syncthreads();
+    CB_TRACE2(2);
     double* rc = r + cb_ro(tid);
     // DQRQH: R -> upper Hessenberg, thread t owns column t
     {
@@ -311,6 +344,7 @@ NLB_DEV void cb_qr_rank1_update(double* q, double* r, const double* u, const dou
         }
         rc[0] = t;
     }
+    CB_TRACE2(3);
     // DQROT('B'): Q <- Q G^T, last rotation first; thread t owns row t
     {
         double hi = q[tid + (N - 1) * LD];
@@ -323,6 +357,7 @@ NLB_DEV void cb_qr_rank1_update(double* q, double* r, const double* u, const dou
         q[tid] = hi;
     }
     __syncthreads();
+    CB_TRACE2(4);
     // first row of R += w(1) v^T
     rc[0] = rc[0] + w0 * v[tid];
     // DQHQR: back to triangular.  Rotation j is generated from column j once rotations 0..j-1 have been applied to
@@ -342,7 +377,7 @@ NLB_DEV void cb_qr_rank1_update(double* q, double* r, const double* u, const dou
                     double c = 0.0, s = 0.0;
                     if (tid == j) {
                         double rjj;
-                        dlartg(t, rn, c, s, rjj);
+                        cb_dlartg(t, rn, c, s, rjj);
                         cs[j] = c; sn[j] = s;
                         rc[j] = rjj;
                         rc[j + 1] = 0.0;
@@ -370,6 +405,7 @@ NLB_DEV void cb_qr_rank1_update(double* q, double* r, const double* u, const dou
         if (tid == N - 1) rc[N - 1] = t;
         if (NWARP == 1) __syncthreads();
     }
+    CB_TRACE2(5);
     // DQROT('F')
     {
         double lo = q[tid];
@@ -436,7 +472,8 @@ coop_broyden_kernel(DevParams p, long long nsys, long long B, double* __restrict
         for (;;) {
             ++iter;
             if (iter > p.max_iter_guard) { flag = 1; break; }
-            if (restart) {
+CB_TRACE(0);
+                        if (restart) {
                 // forward-difference Jacobian, column by column (vfh_jac_fcn :262-275)
                 xp[tid] = x[tid];
                 __syncthreads();
@@ -455,7 +492,9 @@ coop_broyden_kernel(DevParams p, long long nsys, long long B, double* __restrict
                 }
                 ++njac;
                 __syncthreads();
+                CB_TRACE(1);
                 cb_qr_full<N>(brow, q, r, tau, cs, tid);
+                CB_TRACE(2);
                 jcount = 0;
             } else {
                 df[tid] = fvec[tid] - fvold[tid];
@@ -489,10 +528,13 @@ coop_broyden_kernel(DevParams p, long long nsys, long long B, double* __restrict
                     }
                 }
                 __syncthreads();
-                cb_qr_rank1_update<N>(q, r, s, dx, w, cs, sn, tid);
+                CB_TRACE(3);
+                cb_qr_rank1_update<N>(q, r, s, dx, w, cs, sn, tid, iter);
+                CB_TRACE(4);
                 ++jcount;
             }
 
+            CB_TRACE(5);
             // gradient B^T F -> dx ; save state ; -Q^T F -> df
             {
                 double t1 = 0.0, t2 = 0.0;
@@ -521,6 +563,7 @@ coop_broyden_kernel(DevParams p, long long nsys, long long B, double* __restrict
             }
             fold = f;
             __syncthreads();
+            CB_TRACE(6);
             // R step = -Q^T F (DTRSV upper, no-trans, non-unit): a chain of N divisions.  Thread i keeps entry i in a
             // register; the warp that owns rows 32w..32w+31 runs its 32 links with the pivot entry passed by shuffle
             // (every lane forms the same quotient), then publishes them, and the warps above it apply those 32 columns
@@ -531,6 +574,9 @@ coop_broyden_kernel(DevParams p, long long nsys, long long B, double* __restrict
                 const unsigned mask = cb_mask<N>();
                 const int wid = tid >> 5;
                 double v = df[tid];
+                // the diagonal and its correctly rounded reciprocal, formed by all threads at once before the chain
+                const double dg = r[cb_ro(tid) + tid];
+                const double dy = 1.0 / dg;
 #pragma unroll 1
                 for (int wv = NWARP - 1; wv >= 0; --wv) {
                     const int j0 = 32 * wv;
@@ -540,9 +586,10 @@ coop_broyden_kernel(DevParams p, long long nsys, long long B, double* __restrict
 #pragma unroll 1
                         for (int j = j1; j >= j0; --j) {
                             const double xj = __shfl_sync(mask, v, j & 31);
+                            const double dj = __shfl_sync(mask, dg, j & 31), yj = __shfl_sync(mask, dy, j & 31);
                             if (xj != 0.0) {
                                 const double* rcol = r + cb_ro(j);
-                                const double t = xj / rcol[j];
+                                const double t = nl_div_by_rcp(xj, dj, yj);     // == xj / r(j,j)
                                 if (tid < j) v = v - t * rcol[tid];
                                 if (tid == j) v = t;
                                 nz |= 1u << (j & 31);
@@ -565,6 +612,7 @@ coop_broyden_kernel(DevParams p, long long nsys, long long B, double* __restrict
                 __syncthreads();
             }
 
+            CB_TRACE(7);
             double temp = cb_dot<N>(dx, df);
             if (temp >= 0.0) { restart = true; continue; }
 
@@ -578,6 +626,7 @@ coop_broyden_kernel(DevParams p, long long nsys, long long B, double* __restrict
                     if (mag != 0.0 && mag > stpmax) df[tid] = (stpmax / mag) * df[tid];
                     __syncthreads();
                 }
+                CB_TRACE(8);
                 // ls_search_mimo
                 int ls_status = NLB_NO_ERROR, ls_eval = 0, niter = 0;
                 const double slope = cb_dot<N>(dx, df);
@@ -634,6 +683,7 @@ coop_broyden_kernel(DevParams p, long long nsys, long long B, double* __restrict
                 ++neval;
             }
 
+            CB_TRACE(9);
             // test_convergence(x, xold, fvec, dx, lg = .false.)
             bool check = false;
             xcnvrg = false; fcnvrg = false; gcnvrg = false;
@@ -648,6 +698,7 @@ coop_broyden_kernel(DevParams p, long long nsys, long long B, double* __restrict
             }
             (void)gtol;
             if (check) break;
+            CB_TRACE(10);
             restart = (jcount >= p.jacobian_interval);
             if (neval >= p.max_fcn_evals) { flag = 1; break; }
             __syncthreads();

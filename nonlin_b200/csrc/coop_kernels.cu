@@ -302,3 +302,9 @@ extern "C" int nlb_debug_tlm_trace(long long* stamps, int* counts) {
     return 0;
 }
 #endif
+
+#ifdef NLB_CB_TRACE
+extern "C" int nlb_debug_cb_trace(long long* stamps) {
+    return cudaMemcpyFromSymbol(stamps, nlb::cb_trace_buf, sizeof(long long) * 64 * 32) != cudaSuccess;
+}
+#endif

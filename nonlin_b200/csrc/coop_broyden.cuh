@@ -574,9 +574,12 @@ CB_TRACE(0);
                 const unsigned mask = cb_mask<N>();
                 const int wid = tid >> 5;
                 double v = df[tid];
-                // the diagonal and its correctly rounded reciprocal, formed by all threads at once before the chain
+                // the diagonal and its correctly rounded reciprocal, formed by all threads at once before the chain and
+                // published (w, cs are free here): a link then costs one shuffle, five FMAs and the update
                 const double dg = r[cb_ro(tid) + tid];
-                const double dy = 1.0 / dg;
+                w[tid] = dg;
+                cs[tid] = 1.0 / dg;
+                __syncthreads();
 #pragma unroll 1
                 for (int wv = NWARP - 1; wv >= 0; --wv) {
                     const int j0 = 32 * wv;
@@ -585,15 +588,14 @@ CB_TRACE(0);
                         unsigned nz = 0;
 #pragma unroll 1
                         for (int j = j1; j >= j0; --j) {
+                            const double dj = w[j], yj = cs[j];
+                            const double rij = r[cb_ro(j) + (tid < j ? tid : j)];
                             const double xj = __shfl_sync(mask, v, j & 31);
-                            const double dj = __shfl_sync(mask, dg, j & 31), yj = __shfl_sync(mask, dy, j & 31);
-                            if (xj != 0.0) {
-                                const double* rcol = r + cb_ro(j);
-                                const double t = nl_div_by_rcp(xj, dj, yj);     // == xj / r(j,j)
-                                if (tid < j) v = v - t * rcol[tid];
-                                if (tid == j) v = t;
-                                nz |= 1u << (j & 31);
-                            }
+                            const bool live = xj != 0.0;               // the reference skips a zero entry altogether
+                            const double t = nl_div_by_rcp(xj, dj, yj);     // == xj / r(j,j)
+                            if (live && tid < j) v = v - t * rij;
+                            if (live && tid == j) v = t;
+                            nz |= (live ? 1u : 0u) << (j & 31);
                         }
                         df[tid] = v;
                         if ((tid & 31) == 0) solved_nz[wv] = nz;

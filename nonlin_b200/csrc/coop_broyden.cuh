@@ -46,7 +46,7 @@ struct CoopBroydenSmem {
     static constexpr int MAT = N * LD;
     static constexpr int RPK = N * (N + 3) / 2;   // packed upper-Hessenberg storage of R
     static constexpr int NVEC = 10;
-    static constexpr int STAGE = 4;     // rows of B published at a time for B^T f (aliases s, w, cs, sn)
+    static constexpr int STAGE = 8;     // rows of B published at a time for B^T f (aliases xold ... sn, all dead there)
     static constexpr int SLD = N + 1;   // their stride (conflict-free for the four owners writing side by side)
     static constexpr size_t BYTES = ((size_t)MAT + RPK + NVEC * (size_t)N + 8) * sizeof(double);
 };
@@ -445,7 +445,8 @@ coop_broyden_kernel(DevParams p, long long nsys, long long B, double* __restrict
     double* w = s + N;
     double* cs = w + N;
     double* sn = cs + N;
-    double* stage = s;        // STAGE x SLD staging rows for B^T f: s, w, cs, sn (+ 8 spare doubles) are dead by then
+    double* stage = xold;     // STAGE x SLD staging rows for B^T f: xold, fvold, dx, df, s, w, cs, sn (+ 8 spare doubles)
+                              // are all dead by then (the old state is about to be overwritten, the update is over)
     double* tau = w;          // Householder scalars: only live inside the refactorisation
     double* xp = s;           // perturbed copy of x for the forward differences: only live there too
     double brow[N];           // row `tid` of the Broyden matrix B
